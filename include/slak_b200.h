@@ -1,0 +1,117 @@
+/*
+ * slak_b200.h -- C ABI of libslak_b200.so: the B200 (sm_100a) implementation of
+ * SLaK's large-kernel depthwise-convolution hot path.
+ *
+ * Every entry point is a plain-C function over raw device pointers and sizes
+ * (no torch types).  All tensors are dense NCHW, contiguous.  Every call
+ * enqueues work on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ * default stream) and returns immediately; the return value is 0 on success or
+ * a negative slak_status code, and slak_last_error() gives a message.  Nothing
+ * calls exit(): the reference wrappers abort the process on a CUDA/CUTLASS
+ * error (forward_fp32.cu:173-192), these return a code instead.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   cutlass/examples/19_large_depthwise_conv2d_torch_extension/frontend.h:3-10
+ *     forward_fp32/fp16            -> slak_dwconv2d_fwd
+ *     backward_data_fp32/fp16      -> slak_dwconv2d_bwd_data
+ *     backward_filter_fp32/fp16    -> slak_dwconv2d_bwd_filter
+ *   models/SLaK.py:89-100 (ReparamLargeKernelConv.forward, conv + BN + sum)
+ *                                  -> slak_lk_branches_* / slak_bn_* (fused)
+ *   sparse_core.py:316-333 (Masking.apply_mask) -> slak_mask_apply
+ *   funcs.py:107-114 (magnitude_prune)          -> slak_mask_prune_magnitude
+ */
+#ifndef SLAK_B200_H_
+#define SLAK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SLAK_API
+#else
+#define SLAK_API __attribute__((visibility("default")))
+#endif
+
+/* Element types of activation / gradient tensors. */
+enum slak_dtype { SLAK_F32 = 0, SLAK_F16 = 1, SLAK_BF16 = 2 };
+
+/* Status codes (return values are 0 or negative). */
+enum slak_status {
+  SLAK_OK = 0,
+  SLAK_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, even kernel ... */
+  SLAK_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels cover */
+  SLAK_ERR_CUDA = -3,         /* a CUDA runtime call failed (see slak_last_error) */
+  SLAK_ERR_WORKSPACE = -4     /* workspace too small */
+};
+
+/* Library version: major*10000 + minor*100 + patch. */
+SLAK_API int slak_version(void);
+/* Thread-local message for the last failing call on this thread. */
+SLAK_API const char* slak_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is visible, else 0. */
+SLAK_API int slak_device_ok(void);
+
+/* ---------------------------------------------------------------------------
+ * Depthwise conv2d, stride 1, dilation 1, "same" padding (kh/2, kw/2),
+ * cross-correlation:
+ *   y[n,c,p,q] = sum_{r,s} x[n,c,p+r-kh/2,q+s-kw/2] * w[c,0,r,s]
+ * (forward_fp32.cu:135-144,227).  kh and kw must be odd.
+ *   x, y : [N,C,H,W] of `dtype`
+ *   w    : [C,1,kh,kw] of `wdtype` (SLAK_F32, or the same as `dtype`).  When
+ *          dtype is a 16-bit type the weights are rounded to it before use
+ *          (what autocast's cast_inputs does to the reference's FP16 path,
+ *          depthwise_conv2d_implicit_gemm.py:35) and products accumulate in fp32.
+ * ------------------------------------------------------------------------- */
+SLAK_API int slak_dwconv2d_fwd(const void* x, const void* w, void* y,
+                               int N, int C, int H, int W, int kh, int kw,
+                               int dtype, int wdtype, void* stream);
+
+/* dx[n,c,h,w] = sum_{r,s} dy[n,c,h-r+kh/2,w-s+kw/2] * w[c,0,r,s]
+ * (backward_data_fp32.cu:199-263). */
+SLAK_API int slak_dwconv2d_bwd_data(const void* dy, const void* w, void* dx,
+                                    int N, int C, int H, int W, int kh, int kw,
+                                    int dtype, int wdtype, void* stream);
+
+/* dw[c,0,r,s] = sum_{n,p,q} dy[n,c,p,q] * x[n,c,p+r-kh/2,q+s-kw/2], fp32 output
+ * whatever the input dtype (backward_filter_fp16.cu:18,187).  Deterministic:
+ * per-CTA partial sums go to `workspace` and are reduced in a fixed order (the
+ * reference uses fp32 atomicAdd, dwconv2d_direct_epilogue_simt.h:160-185).
+ * workspace must hold slak_dwconv2d_bwd_filter_workspace(...) bytes. */
+SLAK_API size_t slak_dwconv2d_bwd_filter_workspace(int N, int C, int H, int W,
+                                                   int kh, int kw, int dtype);
+SLAK_API int slak_dwconv2d_bwd_filter(const void* dy, const void* x, float* dw,
+                                      int N, int C, int H, int W, int kh, int kw,
+                                      int dtype, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Sparse-mask engine (sparse_core.py:316-333, funcs.py:107-114).
+ * ------------------------------------------------------------------------- */
+
+/* One launch over a list of tensors: w_i[j] = w_i[j] * mask_i[j] for every i
+ * (IEEE multiply, so a pruned negative weight becomes -0.0 exactly as
+ * `tensor.data = tensor.data*self.masks[name]` does).  `w_ptrs`, `mask_ptrs`
+ * and `numels` are DEVICE arrays of length `count`; `extra_ptrs` (may be NULL)
+ * is a second list of tensors multiplied by the same masks (SGD momentum
+ * buffers, sparse_core.py:325-326; entries may be NULL). */
+SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs,
+                             float* const* extra_ptrs, const int64_t* numels,
+                             int count, int64_t max_numel, void* stream);
+
+/* Magnitude prune of one layer: zero the mask at the k smallest |w| positions
+ * (ties broken by lower flat index first, like a stable ascending sort).
+ * mask is updated in place; `workspace` needs
+ * slak_mask_prune_workspace(numel) bytes. */
+SLAK_API size_t slak_mask_prune_workspace(int64_t numel);
+SLAK_API int slak_mask_prune_magnitude(const float* w, float* mask, int64_t numel,
+                                       int64_t k, void* workspace,
+                                       size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAK_B200_H_ */

@@ -1,0 +1,84 @@
+"""ctypes binding of libslak_b200.so (the C ABI declared in include/slak_b200.h).
+
+The library is loaded lazily; a missing library or a failing call raises -- there is no
+CPU or PyTorch fallback anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libslak_b200.so")
+
+SLAK_F32, SLAK_F16, SLAK_BF16 = 0, 1, 2
+
+_lib = None
+_lock = threading.Lock()
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/slak_b200.h one to one
+SIGNATURES = {
+    "slak_version": (_i, []),
+    "slak_last_error": (ctypes.c_char_p, []),
+    "slak_device_ok": (_i, []),
+    "slak_dwconv2d_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "slak_dwconv2d_bwd_data": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "slak_dwconv2d_bwd_filter_workspace": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "slak_dwconv2d_bwd_filter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "slak_mask_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "slak_mask_prune_workspace": (_sz, [_i64]),
+    "slak_mask_prune_magnitude": (_i, [_vp, _vp, _i64, _i64, _vp, _sz, _vp]),
+}
+
+
+class SlakError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libslak_b200.so (building is `python -m slak_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise SlakError(
+                f"{LIB_PATH} is missing: build it with `python -m slak_b200.build` "
+                "(there is no CPU fallback for the slak_b200 kernels)")
+        lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().slak_last_error().decode("utf-8", "replace")
+        raise SlakError(f"{what} failed (status {rc}): {msg}")
+
+
+def dtype_code(dtype) -> int:
+    import torch
+    if dtype == torch.float32:
+        return SLAK_F32
+    if dtype == torch.float16:
+        return SLAK_F16
+    if dtype == torch.bfloat16:
+        return SLAK_BF16
+    raise TypeError("Only support fp32, fp16 and bf16, get {}".format(dtype))
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

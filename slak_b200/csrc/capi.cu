@@ -1,0 +1,119 @@
+// extern "C" entry points of libslak_b200.so (see include/slak_b200.h).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace slak {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// dwconv_simt.cu
+int dwconv_simt_fwd(const void* x, const void* w, void* y, int N, int C, int H, int W, int kh, int kw,
+                    int dtype, int wdtype, int flip, cudaStream_t st);
+size_t dwconv_simt_wgrad_workspace(int N, int C, int H, int W, int kh, int kw);
+int dwconv_simt_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int kh,
+                      int kw, int dtype, void* workspace, cudaStream_t st);
+// mask.cu
+int mask_apply(float* const* w_ptrs, const float* const* m_ptrs, float* const* e_ptrs,
+               const int64_t* numels, int count, int64_t max_numel, cudaStream_t st);
+size_t mask_prune_workspace(int64_t n);
+int mask_prune_magnitude(const float* w, float* mask, int64_t n, int64_t k, void* workspace,
+                         cudaStream_t st);
+
+static int check_conv_args(const void* a, const void* b, const void* c, int N, int C, int H, int W,
+                           int kh, int kw, int dtype, int wdtype) {
+  SLAK_REQUIRE(a && b && c, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, SLAK_ERR_BAD_ARG,
+               "non-positive tensor size N=%d C=%d H=%d W=%d", N, C, H, W);
+  SLAK_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1), SLAK_ERR_BAD_ARG,
+               "kernel %dx%d: both sides must be odd (same-size output needs pad=k/2)", kh, kw);
+  SLAK_REQUIRE(dtype == SLAK_F32 || dtype == SLAK_F16 || dtype == SLAK_BF16, SLAK_ERR_BAD_ARG,
+               "Only support fp32, fp16 and bf16, get dtype code %d", dtype);
+  SLAK_REQUIRE(wdtype == SLAK_F32 || wdtype == dtype, SLAK_ERR_BAD_ARG,
+               "weight dtype %d must be fp32 or equal to the activation dtype %d", wdtype, dtype);
+  SLAK_REQUIRE(C <= 65535 * 32 && (long long)H * W < (1ll << 30), SLAK_ERR_UNSUPPORTED,
+               "tensor too large: C=%d H=%d W=%d", C, H, W);
+  return SLAK_OK;
+}
+
+}  // namespace slak
+
+using namespace slak;
+
+extern "C" {
+
+SLAK_API int slak_version(void) { return 100; }
+
+SLAK_API const char* slak_last_error(void) { return g_err; }
+
+SLAK_API int slak_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+SLAK_API int slak_dwconv2d_fwd(const void* x, const void* w, void* y, int N, int C, int H, int W,
+                               int kh, int kw, int dtype, int wdtype, void* stream) {
+  int rc = check_conv_args(x, w, y, N, C, H, W, kh, kw, dtype, wdtype);
+  if (rc) return rc;
+  return dwconv_simt_fwd(x, w, y, N, C, H, W, kh, kw, dtype, wdtype, /*flip=*/0, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_dwconv2d_bwd_data(const void* dy, const void* w, void* dx, int N, int C, int H,
+                                    int W, int kh, int kw, int dtype, int wdtype, void* stream) {
+  int rc = check_conv_args(dy, w, dx, N, C, H, W, kh, kw, dtype, wdtype);
+  if (rc) return rc;
+  return dwconv_simt_fwd(dy, w, dx, N, C, H, W, kh, kw, dtype, wdtype, /*flip=*/1, (cudaStream_t)stream);
+}
+
+SLAK_API size_t slak_dwconv2d_bwd_filter_workspace(int N, int C, int H, int W, int kh, int kw,
+                                                   int dtype) {
+  (void)dtype;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0) return 0;
+  return dwconv_simt_wgrad_workspace(N, C, H, W, kh, kw);
+}
+
+SLAK_API int slak_dwconv2d_bwd_filter(const void* dy, const void* x, float* dw, int N, int C, int H,
+                                      int W, int kh, int kw, int dtype, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  int rc = check_conv_args(dy, x, dw, N, C, H, W, kh, kw, dtype, dtype);
+  if (rc) return rc;
+  size_t need = dwconv_simt_wgrad_workspace(N, C, H, W, kh, kw);
+  SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE,
+               "bwd_filter workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  return dwconv_simt_wgrad(dy, x, dw, N, C, H, W, kh, kw, dtype, workspace, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs,
+                             float* const* extra_ptrs, const int64_t* numels, int count,
+                             int64_t max_numel, void* stream) {
+  SLAK_REQUIRE(count >= 0, SLAK_ERR_BAD_ARG, "negative tensor count");
+  if (count == 0) return SLAK_OK;
+  SLAK_REQUIRE(w_ptrs && mask_ptrs && numels, SLAK_ERR_BAD_ARG, "null pointer table");
+  SLAK_REQUIRE(count <= 65535, SLAK_ERR_UNSUPPORTED, "too many tensors in one launch: %d", count);
+  return mask_apply(w_ptrs, mask_ptrs, extra_ptrs, numels, count, max_numel, (cudaStream_t)stream);
+}
+
+SLAK_API size_t slak_mask_prune_workspace(int64_t numel) { return mask_prune_workspace(numel); }
+
+SLAK_API int slak_mask_prune_magnitude(const float* w, float* mask, int64_t numel, int64_t k,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  SLAK_REQUIRE(w && mask, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(numel >= 0 && numel < (1ll << 32), SLAK_ERR_UNSUPPORTED, "numel %lld out of range",
+               (long long)numel);
+  SLAK_REQUIRE(workspace && workspace_bytes >= mask_prune_workspace(numel), SLAK_ERR_WORKSPACE,
+               "prune workspace too small");
+  return mask_prune_magnitude(w, mask, numel, k, workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Shared helpers for the slak_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/slak_b200.h"
+
+namespace slak {
+
+// ---- thread-local error message ------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define SLAK_CUDA_TRY(expr)                                                        \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      slak::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                      __FILE__, __LINE__);                                         \
+      return SLAK_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+#define SLAK_REQUIRE(cond, code, ...)                                              \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      slak::set_error(__VA_ARGS__);                                                \
+      return (code);                                                               \
+    }                                                                              \
+  } while (0)
+
+// ---- element conversion --------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// round an fp32 weight to the activation type and back (autocast semantics)
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32<T>(from_f32<T>(v)); }
+
+static inline int dtype_size(int dtype) { return dtype == SLAK_F32 ? 4 : 2; }
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+}  // namespace slak

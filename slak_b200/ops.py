@@ -1,0 +1,121 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the stream,
+the kernels do the work.  Everything here requires CUDA tensors; nothing falls back.
+
+Mirrors the reference operator boundary:
+  cutlass/examples/19_large_depthwise_conv2d_torch_extension/frontend.h:3-10   (the 6 functions)
+  depthwise_conv2d_implicit_gemm.py:14-49                                      (autograd glue)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _check_input(t: torch.Tensor, name: str) -> None:
+    # same checks as CHECK_INPUT in forward_fp32.cu:194-196
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _conv_dims(x: torch.Tensor, w: torch.Tensor):
+    if x.dim() != 4 or w.dim() != 4 or w.size(1) != 1 or w.size(0) != x.size(1):
+        raise RuntimeError(f"expected x [N,C,H,W] and weight [C,1,kh,kw], got {tuple(x.shape)} and {tuple(w.shape)}")
+    N, C, H, W = x.shape
+    return N, C, H, W, w.size(2), w.size(3)
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def dwconv2d_forward(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """y = depthwise cross-correlation of x with w, stride 1, padding (kh//2, kw//2)."""
+    _check_input(x, "input")
+    _check_input(w, "weight")
+    N, C, H, W, kh, kw = _conv_dims(x, w)
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        rc = lib.slak_dwconv2d_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, C, H, W, kh, kw,
+                                   _lib.dtype_code(x.dtype), _lib.dtype_code(w.dtype),
+                                   _lib.current_stream_ptr())
+    _lib.check(rc, "slak_dwconv2d_fwd")
+    return y
+
+
+def dwconv2d_backward_data(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    _check_input(dy, "grad")
+    _check_input(w, "weight")
+    N, C, H, W, kh, kw = _conv_dims(dy, w)
+    dx = torch.empty_like(dy)
+    lib = _lib.load()
+    with torch.cuda.device(dy.device):
+        rc = lib.slak_dwconv2d_bwd_data(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), N, C, H, W, kh, kw,
+                                        _lib.dtype_code(dy.dtype), _lib.dtype_code(w.dtype),
+                                        _lib.current_stream_ptr())
+    _lib.check(rc, "slak_dwconv2d_bwd_data")
+    return dx
+
+
+def dwconv2d_backward_filter(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dw in fp32 whatever the activation dtype (backward_filter_fp16.cu:18,187); `w` only gives the shape."""
+    _check_input(dy, "grad")
+    _check_input(x, "input")
+    if dy.dtype != x.dtype or dy.shape != x.shape:
+        raise RuntimeError("grad and input must have the same dtype and shape")
+    N, C, H, W, kh, kw = _conv_dims(x, w)
+    dw = torch.empty((C, 1, kh, kw), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    code = _lib.dtype_code(x.dtype)
+    need = lib.slak_dwconv2d_bwd_filter_workspace(N, C, H, W, kh, kw, code)
+    with torch.cuda.device(x.device):
+        ws = _workspace(need, x.device)
+        rc = lib.slak_dwconv2d_bwd_filter(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), N, C, H, W, kh, kw,
+                                          code, ws.data_ptr(), ws.numel(), _lib.current_stream_ptr())
+    _lib.check(rc, "slak_dwconv2d_bwd_filter")
+    return dw
+
+
+class DepthwiseConv2dFunction(torch.autograd.Function):
+    """One autograd node for all dtypes.  dtype of y = dtype of x; the weight stays the fp32
+    Parameter and is rounded to x's dtype inside the kernel (what
+    custom_fwd(cast_inputs=torch.float16) does to the reference's FP16 path,
+    depthwise_conv2d_implicit_gemm.py:33-38); dw comes back fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous()
+        w = w.contiguous()
+        ctx.save_for_backward(x, w)
+        return dwconv2d_forward(x, w)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w = ctx.saved_tensors
+        grad = grad.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = dwconv2d_backward_data(grad, w)
+        if ctx.needs_input_grad[1]:
+            dw = dwconv2d_backward_filter(grad, x, w).to(w.dtype)
+        return dx, dw
+
+
+def depthwise_conv2d(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise TypeError("Only support fp32, fp16 and bf16, get {}".format(x.dtype))
+    if w.dtype != torch.float32 and w.dtype != x.dtype:
+        w = w.to(x.dtype)
+    return DepthwiseConv2dFunction.apply(x, w)
