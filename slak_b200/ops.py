@@ -29,6 +29,38 @@ def _conv_dims(x: torch.Tensor, w: torch.Tensor):
 
 _ws_cache: dict = {}
 
+# ---- instrumentation used by bench.py (launch accounting + CUDA-event timing of one kernel) ----
+_launches = 0
+_prof = {"match": None, "events": []}
+
+
+def launch_count() -> int:
+    """Number of slak_b200 CUDA kernels launched so far by this process."""
+    return _launches
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
+
+
+def profile_reset(match) -> None:
+    """match = dict(N,C,H,W,kh,kw) of the forward launches to bracket with CUDA events, or None."""
+    _prof["match"] = match
+    _prof["events"] = []
+
+
+def profile_collect():
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in _prof["events"])
+    return {"count": len(_prof["events"]), "ms_total": ms}
+
+
+def _profiled(N, C, H, W, kh, kw, dtype):
+    m = _prof["match"]
+    return (m is not None and dtype == torch.bfloat16 and
+            (N, C, H, W, kh, kw) == (m["N"], m["C"], m["H"], m["W"], m["kh"], m["kw"]))
+
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
     """Per-(device, stream) scratch buffer, grown on demand."""
@@ -47,11 +79,19 @@ def dwconv2d_forward(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     N, C, H, W, kh, kw = _conv_dims(x, w)
     y = torch.empty_like(x)
     lib = _lib.load()
+    timed = _profiled(N, C, H, W, kh, kw, x.dtype)
     with torch.cuda.device(x.device):
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         rc = lib.slak_dwconv2d_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, C, H, W, kh, kw,
                                    _lib.dtype_code(x.dtype), _lib.dtype_code(w.dtype),
                                    _lib.current_stream_ptr())
+        if timed:
+            ev[1].record()
+            _prof["events"].append(ev)
     _lib.check(rc, "slak_dwconv2d_fwd")
+    _count(1)
     return y
 
 
@@ -66,6 +106,7 @@ def dwconv2d_backward_data(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
                                         _lib.dtype_code(dy.dtype), _lib.dtype_code(w.dtype),
                                         _lib.current_stream_ptr())
     _lib.check(rc, "slak_dwconv2d_bwd_data")
+    _count(1)
     return dx
 
 
@@ -85,6 +126,7 @@ def dwconv2d_backward_filter(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor)
         rc = lib.slak_dwconv2d_bwd_filter(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), N, C, H, W, kh, kw,
                                           code, ws.data_ptr(), ws.numel(), _lib.current_stream_ptr())
     _lib.check(rc, "slak_dwconv2d_bwd_filter")
+    _count(2)   # partial-sum kernel + fixed-order reduce
     return dw
 
 
