@@ -89,6 +89,21 @@ SLAK_API int slak_dwconv2d_bwd_filter(const void* dy, const void* x, float* dw,
                                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * The three depthwise branches of ReparamLargeKernelConv.forward (models/SLaK.py:89-100,
+ * Decom=True) in one call, x read once:
+ *   y1 = dwconv_{KL x KS}(x, w1)   y2 = dwconv_{KS x KL}(x, w2)   y3 = dwconv_{KS x KS}(x, w3)
+ * w1 [C,1,KL,KS], w2 [C,1,KS,KL], w3 [C,1,KS,KS] are the fp32 Parameters (rounded to `dtype`
+ * inside, as in slak_dwconv2d_fwd).  For bf16 tensors with KS == 5, 8 <= H,W <= 62 and
+ * W % 8 == 0 this is ONE tcgen05 (tensor-core, banded-Toeplitz GEMM) kernel; every other
+ * case runs the three CUDA-core kernels back to back.  w3/y3 may be NULL (no small branch,
+ * models/SLaK.py:85).  slak_lk_branches_uses_tc() reports which path a shape takes.
+ * ------------------------------------------------------------------------- */
+SLAK_API int slak_lk_branches_uses_tc(int N, int C, int H, int W, int KL, int KS, int dtype);
+SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w2, const float* w3,
+                                  void* y1, void* y2, void* y3, int N, int C, int H, int W,
+                                  int KL, int KS, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Sparse-mask engine (sparse_core.py:316-333, funcs.py:107-114).
  * ------------------------------------------------------------------------- */
 

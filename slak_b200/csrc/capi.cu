@@ -20,6 +20,12 @@ int dwconv_simt_fwd(const void* x, const void* w, void* y, int N, int C, int H, 
 size_t dwconv_simt_wgrad_workspace(int N, int C, int H, int W, int kh, int kw);
 int dwconv_simt_wgrad(const void* dy, const void* x, float* dw, int N, int C, int H, int W, int kh,
                       int kw, int dtype, void* workspace, cudaStream_t st);
+// dwconv_tc_fwd.cu
+namespace tc {
+bool lk3_tc_supported(int N, int C, int H, int W, int KL);
+int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
+               int N, int C, int H, int W, int KL, cudaStream_t st);
+}
 // mask.cu
 int mask_apply(float* const* w_ptrs, const float* const* m_ptrs, float* const* e_ptrs,
                const int64_t* numels, int count, int64_t max_numel, cudaStream_t st);
@@ -92,6 +98,27 @@ SLAK_API int slak_dwconv2d_bwd_filter(const void* dy, const void* x, float* dw, 
   SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE,
                "bwd_filter workspace too small: %zu < %zu bytes", workspace_bytes, need);
   return dwconv_simt_wgrad(dy, x, dw, N, C, H, W, kh, kw, dtype, workspace, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_lk_branches_uses_tc(int N, int C, int H, int W, int KL, int KS, int dtype) {
+  return (dtype == SLAK_BF16 && KS == 5 && N > 0 && C > 0 && tc::lk3_tc_supported(N, C, H, W, KL)) ? 1 : 0;
+}
+
+SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w2, const float* w3,
+                                  void* y1, void* y2, void* y3, int N, int C, int H, int W, int KL,
+                                  int KS, int dtype, void* stream) {
+  int rc = check_conv_args(x, w1, y1, N, C, H, W, KL, KS, dtype, SLAK_F32);
+  if (rc) return rc;
+  SLAK_REQUIRE(w2 && y2, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE((w3 == nullptr) == (y3 == nullptr), SLAK_ERR_BAD_ARG, "w3 and y3 must both be given or both be NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w3 && slak_lk_branches_uses_tc(N, C, H, W, KL, KS, dtype))
+    return tc::lk3_fwd_tc(x, w1, w2, w3, y1, y2, y3, N, C, H, W, KL, st);
+  rc = dwconv_simt_fwd(x, w1, y1, N, C, H, W, KL, KS, dtype, SLAK_F32, 0, st);
+  if (rc) return rc;
+  rc = dwconv_simt_fwd(x, w2, y2, N, C, H, W, KS, KL, dtype, SLAK_F32, 0, st);
+  if (rc || !w3) return rc;
+  return dwconv_simt_fwd(x, w3, y3, N, C, H, W, KS, KS, dtype, SLAK_F32, 0, st);
 }
 
 SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs,

@@ -161,3 +161,37 @@ def depthwise_conv2d(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     if w.dtype != torch.float32 and w.dtype != x.dtype:
         w = w.to(x.dtype)
     return DepthwiseConv2dFunction.apply(x, w)
+
+
+# ---- fused three-branch forward (models/SLaK.py:89-100) ------------------------------------
+def lk_branches_uses_tc(x: torch.Tensor, KL: int, KS: int) -> bool:
+    N, C, H, W = x.shape
+    return bool(_lib.load().slak_lk_branches_uses_tc(N, C, H, W, KL, KS, _lib.dtype_code(x.dtype)))
+
+
+def lk_branches_forward(x, w1, w2, w3=None):
+    """(y1, y2, y3) = (dwconv_{KLxKS}, dwconv_{KSxKL}, dwconv_{KSxKS})(x) with the fp32 Parameters
+    w1 [C,1,KL,KS], w2 [C,1,KS,KL], w3 [C,1,KS,KS] (or None).  One tcgen05 kernel when the shape
+    allows it (see slak_b200.h), otherwise the CUDA-core kernels."""
+    _check_input(x, "input")
+    for t, nm in ((w1, "w1"), (w2, "w2")) + (((w3, "w3"),) if w3 is not None else ()):
+        _check_input(t, nm)
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{nm} must be the fp32 parameter")
+    N, C, H, W = x.shape
+    KL, KS = w1.size(2), w1.size(3)
+    if tuple(w2.shape) != (C, 1, KS, KL) or (w3 is not None and tuple(w3.shape) != (C, 1, KS, KS)):
+        raise RuntimeError("branch weight shapes do not match [C,1,KL,KS] / [C,1,KS,KL] / [C,1,KS,KS]")
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    y3 = torch.empty_like(x) if w3 is not None else None
+    lib = _lib.load()
+    code = _lib.dtype_code(x.dtype)
+    tc = w3 is not None and lib.slak_lk_branches_uses_tc(N, C, H, W, KL, KS, code)
+    with torch.cuda.device(x.device):
+        rc = lib.slak_lk_branches_fwd(x.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                                      w3.data_ptr() if w3 is not None else None,
+                                      y1.data_ptr(), y2.data_ptr(), y3.data_ptr() if y3 is not None else None,
+                                      N, C, H, W, KL, KS, code, _lib.current_stream_ptr())
+    _lib.check(rc, "slak_lk_branches_fwd")
+    _count(1 if tc else (3 if w3 is not None else 2))
+    return y1, y2, y3
