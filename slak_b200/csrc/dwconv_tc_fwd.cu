@@ -29,7 +29,8 @@
 namespace slak {
 namespace tc {
 
-constexpr int kStages = 2;
+constexpr int kStages = 3;                       // X (natural) slots in flight
+constexpr int kTStages = 1;                      // X^T slots (refilled in the shadow of the b2|b3 MMAs)
 constexpr int kAccBufs = 2;
 constexpr int kPlaneBytes = 64 * 128;            // one 64x64 bf16 tile
 constexpr int kUnitBytes = 2 * kPlaneBytes;      // two stacked planes
@@ -41,7 +42,7 @@ constexpr int kOffToep1 = 0;
 constexpr int kOffToep23 = kOffToep1 + kToep1Bytes;
 constexpr int kOffXN = kOffToep23 + kToep23Bytes;
 constexpr int kOffXT = kOffXN + kStages * kXSlot;
-constexpr int kOffY1 = kOffXT + kStages * kXSlot;          // 16 KB staging for the y1 transpose
+constexpr int kOffY1 = kOffXT + kTStages * kXSlot;         // 16 KB staging for the y1 transpose
 constexpr int kOffBar = kOffY1 + kUnitBytes;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;           // + alignment slack
 constexpr int kTmemCols = 512;
@@ -76,21 +77,25 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   const int u_end = (int)(((long long)P.pairs_per_c * (split + 1)) / P.splits);
   const int KL = P.KL, pad = KL / 2, H = P.H, W = P.W;
 
-  // barriers: [0,2) xn_full [2,4) xn_empty [4,6) xt_full [6,8) xt_empty [8,10) acc_full [10,12) acc_empty
+  // barriers
+  constexpr int B_XN_FULL = 0, B_XN_EMPTY = kStages, B_XT_FULL = 2 * kStages, B_XT_EMPTY = B_XT_FULL + kTStages,
+                B_ACC_FULL = B_XT_EMPTY + kTStages, B_ACC_EMPTY = B_ACC_FULL + kAccBufs;
   const uint32_t bar0 = base + kOffBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 128);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(BAR(0 + s), 1);                         // TMA expect_tx arrive
-      mbar_init(BAR(2 + s), 1 + kNumTransposerWarps);   // MMA commit + transposers done reading
-      mbar_init(BAR(4 + s), kNumTransposerWarps);       // transposers wrote X^T
-      mbar_init(BAR(6 + s), 1);                         // MMA commit
+      mbar_init(BAR(B_XN_FULL + s), 1);                          // TMA expect_tx arrive
+      mbar_init(BAR(B_XN_EMPTY + s), 1 + kNumTransposerWarps);   // MMA commit + transposers done reading
+    }
+    for (int s = 0; s < kTStages; ++s) {
+      mbar_init(BAR(B_XT_FULL + s), kNumTransposerWarps);        // transposers wrote X^T
+      mbar_init(BAR(B_XT_EMPTY + s), 1);                         // MMA commit
     }
     for (int a = 0; a < kAccBufs; ++a) {
-      mbar_init(BAR(8 + a), 1);                         // MMA commit
-      mbar_init(BAR(10 + a), 4);                        // one arrival per epilogue warp
+      mbar_init(BAR(B_ACC_FULL + a), 1);                         // MMA commit
+      mbar_init(BAR(B_ACC_EMPTY + a), 4);                        // one arrival per epilogue warp
     }
     mbar_fence_init();
     tma_prefetch_desc(&xmap);
@@ -99,7 +104,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   // ---- zero the pads of the X / X^T slots and build the Toeplitz operands (all threads) -------
   {
     uint4 z = make_uint4(0, 0, 0, 0);
-    for (int s = 0; s < 2 * kStages; ++s) {
+    for (int s = 0; s < kStages + kTStages; ++s) {
       uint8_t* slot = sm + kOffXN + s * kXSlot;
       for (int i = tid; i < kPad / 16; i += 256) {
         reinterpret_cast<uint4*>(slot)[i] = z;
@@ -164,13 +169,13 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     if (elect_one()) {
       for (int i = 0; i < n_units; ++i) {
         const int st = i % kStages, ph = (i / kStages) & 1;
-        mbar_wait(BAR(2 + st), ph ^ 1);
+        mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
         const int n0 = 2 * (u_begin + i);
         const uint32_t dst = base + kOffXN + st * kXSlot + kPad;
-        mbar_expect_tx(BAR(0 + st), kUnitBytes);
+        mbar_expect_tx(BAR(B_XN_FULL + st), kUnitBytes);
         const int na = n0, nb = min(n0 + 1, P.N - 1);
-        tma_load_3d(dst, &xmap, BAR(0 + st), 0, 0, na * P.C + c);
-        tma_load_3d(dst + kPlaneBytes, &xmap, BAR(0 + st), 0, 0, nb * P.C + c);
+        tma_load_3d(dst, &xmap, BAR(B_XN_FULL + st), 0, 0, na * P.C + c);
+        tma_load_3d(dst + kPlaneBytes, &xmap, BAR(B_XN_FULL + st), 0, 0, nb * P.C + c);
       }
     }
   } else if (warp == 1) {
@@ -181,11 +186,12 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       for (int i = 0; i < n_units; ++i) {
         const int st = i % kStages, ph = (i / kStages) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
-        mbar_wait(BAR(10 + ab), aph ^ 1);       // epilogue drained this accumulator buffer
-        mbar_wait(BAR(0 + st), ph);             // X landed
+        const int ts = i % kTStages, tph = (i / kTStages) & 1;
+        mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);   // epilogue drained this accumulator buffer
+        mbar_wait(BAR(B_XN_FULL + st), ph);          // X landed
         tc_fence_after();
         const uint32_t xn = base + kOffXN + st * kXSlot + kPad;
-        const uint32_t xt = base + kOffXT + st * kXSlot + kPad;
+        const uint32_t xt = base + kOffXT + ts * kXSlot + kPad;
         const uint32_t d1 = tmem + ab * kAccCols;
         const uint32_t d23 = d1 + 64;
 #pragma unroll
@@ -196,7 +202,8 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
             const uint32_t b = base + kOffToep23 + r * (128 * 128) + k * 32;
             umma_bf16(d23, umma_desc_k_sw128(a, SLAK_TC_BASE_OFF(a)), umma_desc_k_sw128(b, 0), idesc23, (r | k) != 0);
           }
-        mbar_wait(BAR(4 + st), ph);             // X^T written
+        umma_commit(BAR(B_XN_EMPTY + st));           // X slot free (with the transposers' arrivals)
+        mbar_wait(BAR(B_XT_FULL + ts), tph);         // X^T written
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 5; ++s)
@@ -206,9 +213,8 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
             const uint32_t b = base + kOffToep1 + s * (64 * 128) + k * 32;
             umma_bf16(d1, umma_desc_k_sw128(a, SLAK_TC_BASE_OFF(a)), umma_desc_k_sw128(b, 0), idesc1, (s | k) != 0);
           }
-        umma_commit(BAR(2 + st));               // X slot free (with the transposers' arrivals)
-        umma_commit(BAR(6 + st));               // X^T slot free
-        umma_commit(BAR(8 + ab));               // accumulators ready
+        umma_commit(BAR(B_XT_EMPTY + ts));           // X^T slot free
+        umma_commit(BAR(B_ACC_FULL + ab));           // accumulators ready
       }
     }
   } else if (warp < 4) {
@@ -217,10 +223,11 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     const int m = lane >> 3, kk = lane & 7;     // matrix id within the x4, row within the 8x8 block
     for (int i = 0; i < n_units; ++i) {
       const int st = i % kStages, ph = (i / kStages) & 1;
-      mbar_wait(BAR(0 + st), ph);               // X landed
-      mbar_wait(BAR(6 + st), ph ^ 1);           // previous X^T of this slot consumed
+      const int ts = i % kTStages, tph = (i / kTStages) & 1;
+      mbar_wait(BAR(B_XN_FULL + st), ph);       // X landed
+      mbar_wait(BAR(B_XT_EMPTY + ts), tph ^ 1); // previous X^T of this slot consumed
       const uint32_t xn = base + kOffXN + st * kXSlot + kPad;
-      const uint32_t xt = base + kOffXT + st * kXSlot + kPad;
+      const uint32_t xt = base + kOffXT + ts * kXSlot + kPad;
       for (int it = tw; it < 32; it += kNumTransposerWarps) {
         const int h = it >> 4, bi = (it >> 1) & 7, g = it & 1;
         const int bj = 4 * g + m;
@@ -233,8 +240,8 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(BAR(4 + st));               // X^T ready
-        mbar_arrive(BAR(2 + st));               // done reading X
+        mbar_arrive(BAR(B_XT_FULL + ts));       // X^T ready
+        mbar_arrive(BAR(B_XN_EMPTY + st));      // done reading X
       }
     }
   } else {
@@ -250,7 +257,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       const int n = 2 * (u_begin + i) + half;
       const bool plane_ok = n < P.N;
       const size_t pbase = ((size_t)(plane_ok ? n : 0) * P.C + c) * plane_elems;
-      mbar_wait(BAR(8 + ab), aph);
+      mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
       const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * kAccCols;
       uint32_t v[64];
@@ -262,13 +269,16 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         tmem_ld_wait();
         if (plane_ok && row < H) {
           __nv_bfloat16* yo = (br == 0 ? P.y2 : P.y3) + pbase + (size_t)row * W;
-          for (int ck = 0; ck < wchunks; ++ck) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(v[8 * ck + 0]), __uint_as_float(v[8 * ck + 1]));
-            o.y = pack_bf16(__uint_as_float(v[8 * ck + 2]), __uint_as_float(v[8 * ck + 3]));
-            o.z = pack_bf16(__uint_as_float(v[8 * ck + 4]), __uint_as_float(v[8 * ck + 5]));
-            o.w = pack_bf16(__uint_as_float(v[8 * ck + 6]), __uint_as_float(v[8 * ck + 7]));
-            *reinterpret_cast<uint4*>(yo + 8 * ck) = o;
+#pragma unroll
+          for (int ck = 0; ck < 8; ++ck) {          // static register indices: no local-memory spill
+            if (ck < wchunks) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(v[8 * ck + 0]), __uint_as_float(v[8 * ck + 1]));
+              o.y = pack_bf16(__uint_as_float(v[8 * ck + 2]), __uint_as_float(v[8 * ck + 3]));
+              o.z = pack_bf16(__uint_as_float(v[8 * ck + 4]), __uint_as_float(v[8 * ck + 5]));
+              o.w = pack_bf16(__uint_as_float(v[8 * ck + 6]), __uint_as_float(v[8 * ck + 7]));
+              *reinterpret_cast<uint4*>(yo + 8 * ck) = o;
+            }
           }
         }
       }
@@ -278,7 +288,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(10 + ab));  // accumulators drained
+      if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));  // accumulators drained
 #pragma unroll
       for (int p = 0; p < 64; ++p) {
         const uint32_t off = (uint32_t)(half * 64 + p) * 128 + ((((uint32_t)row >> 3) ^ (p & 7)) << 4) + (row & 7) * 2;

@@ -22,7 +22,8 @@ def test_prune_kernel_equals_stable_sort(numel, k):
     g = torch.Generator().manual_seed(numel + k)
     w = torch.randn(numel, generator=g)
     w[torch.rand(numel, generator=g) < 0.3] = 0.0          # ties at zero, like masked weights
-    w[:: 7] = w[3::7][: len(w[::7])] if numel > 10 else w[::7]   # ties at non-zero magnitudes
+    if numel > 20:
+        w[5:numel // 2] = w[5 + numel // 2 - 5: numel // 2 + numel // 2 - 5].abs().neg()   # ties at non-zero magnitudes
     mask = (torch.rand(numel, generator=g) < 0.8).float()
     want = mask.clone()
     _, idx = torch.sort(torch.abs(w), stable=True)
