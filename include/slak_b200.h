@@ -103,6 +103,23 @@ SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w
                                   void* y1, void* y2, void* y3, int N, int C, int H, int W,
                                   int KL, int KS, int dtype, void* stream);
 
+/* Backward of slak_lk_branches_fwd on the tensor cores; only for shapes where
+ * slak_lk_branches_uses_tc() is 1 (otherwise SLAK_ERR_UNSUPPORTED: call the per-branch
+ * slak_dwconv2d_bwd_* functions).
+ *   bwd_data  : dx = dgrad(dy1,w1) + dgrad(dy2,w2) + dgrad(dy3,w3); `tmp` is a caller-provided
+ *               scratch tensor of the size of dx (holds the 5x5 branch between the two launches).
+ *   bwd_filter: dw1 [C,1,KL,KS], dw2 [C,1,KS,KL], dw3 [C,1,KS,KS] in fp32, deterministic;
+ *               workspace of slak_lk_branches_bwd_filter_workspace() bytes. */
+SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const void* dy3,
+                                       const float* w1, const float* w2, const float* w3,
+                                       void* dx, void* tmp, int N, int C, int H, int W,
+                                       int KL, int KS, int dtype, void* stream);
+SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS);
+SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const void* dy2, const void* dy3,
+                                         float* dw1, float* dw2, float* dw3, int N, int C, int H, int W,
+                                         int KL, int KS, int dtype, void* workspace,
+                                         size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Sparse-mask engine (sparse_core.py:316-333, funcs.py:107-114).
  * ------------------------------------------------------------------------- */

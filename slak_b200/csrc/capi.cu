@@ -25,6 +25,11 @@ namespace tc {
 bool lk3_tc_supported(int N, int C, int H, int W, int KL);
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
                int N, int C, int H, int W, int KL, cudaStream_t st);
+int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
+               int N, int C, int H, int W, int KL, int KN, int flip, cudaStream_t st);
+size_t lk3_wgrad_tc_workspace(int N, int C, int KL);
+int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
+                 float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
 }
 // mask.cu
 int mask_apply(float* const* w_ptrs, const float* const* m_ptrs, float* const* e_ptrs,
@@ -119,6 +124,40 @@ SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w
   rc = dwconv_simt_fwd(x, w2, y2, N, C, H, W, KS, KL, dtype, SLAK_F32, 0, st);
   if (rc || !w3) return rc;
   return dwconv_simt_fwd(x, w3, y3, N, C, H, W, KS, KS, dtype, SLAK_F32, 0, st);
+}
+
+SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const void* dy3, const float* w1,
+                                       const float* w2, const float* w3, void* dx, void* tmp, int N, int C,
+                                       int H, int W, int KL, int KS, int dtype, void* stream) {
+  int rc = check_conv_args(dy1, w1, dx, N, C, H, W, KL, KS, dtype, SLAK_F32);
+  if (rc) return rc;
+  SLAK_REQUIRE(dy2 && dy3 && w2 && w3 && tmp, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(slak_lk_branches_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
+               "fused bwd_data covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = tc::lk_conv_tc(nullptr, nullptr, dy3, w3, nullptr, tmp, N, C, H, W, KL, KS, /*flip=*/1, st);
+  if (rc) return rc;
+  return tc::lk_conv_tc(dy1, w1, dy2, w2, tmp, dx, N, C, H, W, KL, KL, /*flip=*/1, st);
+}
+
+SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS) {
+  (void)H; (void)W; (void)KS;
+  if (N <= 0 || C <= 0 || KL <= 0) return 0;
+  return tc::lk3_wgrad_tc_workspace(N, C, KL);
+}
+
+SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const void* dy2, const void* dy3,
+                                         float* dw1, float* dw2, float* dw3, int N, int C, int H, int W, int KL,
+                                         int KS, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_conv_args(x, dy1, dw1, N, C, H, W, KL, KS, dtype, dtype);
+  if (rc) return rc;
+  SLAK_REQUIRE(dy2 && dy3 && dw2 && dw3, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(slak_lk_branches_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
+               "fused bwd_filter covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
+  const size_t need = tc::lk3_wgrad_tc_workspace(N, C, KL);
+  SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE, "bwd_filter workspace too small: %zu < %zu",
+               workspace_bytes, need);
+  return tc::lk3_wgrad_tc(x, dy1, dy2, dy3, dw1, dw2, dw3, N, C, H, W, KL, workspace, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs,

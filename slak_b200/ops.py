@@ -195,3 +195,42 @@ def lk_branches_forward(x, w1, w2, w3=None):
     _lib.check(rc, "slak_lk_branches_fwd")
     _count(1 if tc else (3 if w3 is not None else 2))
     return y1, y2, y3
+
+
+def lk_branches_backward_data(dy1, dy2, dy3, w1, w2, w3):
+    """dx = dgrad(dy1,w1) + dgrad(dy2,w2) + dgrad(dy3,w3); tensor-core shapes only."""
+    for t, nm in ((dy1, "dy1"), (dy2, "dy2"), (dy3, "dy3"), (w1, "w1"), (w2, "w2"), (w3, "w3")):
+        _check_input(t, nm)
+    N, C, H, W = dy1.shape
+    KL, KS = w1.size(2), w1.size(3)
+    dx = torch.empty_like(dy1)
+    tmp = torch.empty_like(dy1)
+    lib = _lib.load()
+    with torch.cuda.device(dy1.device):
+        rc = lib.slak_lk_branches_bwd_data(dy1.data_ptr(), dy2.data_ptr(), dy3.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                                           w3.data_ptr(), dx.data_ptr(), tmp.data_ptr(), N, C, H, W, KL, KS,
+                                           _lib.dtype_code(dy1.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "slak_lk_branches_bwd_data")
+    _count(2)
+    return dx
+
+
+def lk_branches_backward_filter(x, dy1, dy2, dy3, KL, KS):
+    """(dw1, dw2, dw3) in fp32; tensor-core shapes only."""
+    for t, nm in ((x, "x"), (dy1, "dy1"), (dy2, "dy2"), (dy3, "dy3")):
+        _check_input(t, nm)
+    N, C, H, W = x.shape
+    dev = x.device
+    dw1 = torch.empty((C, 1, KL, KS), dtype=torch.float32, device=dev)
+    dw2 = torch.empty((C, 1, KS, KL), dtype=torch.float32, device=dev)
+    dw3 = torch.empty((C, 1, KS, KS), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    need = lib.slak_lk_branches_bwd_filter_workspace(N, C, H, W, KL, KS)
+    with torch.cuda.device(dev):
+        ws = _workspace(need, dev)
+        rc = lib.slak_lk_branches_bwd_filter(x.data_ptr(), dy1.data_ptr(), dy2.data_ptr(), dy3.data_ptr(), dw1.data_ptr(),
+                                             dw2.data_ptr(), dw3.data_ptr(), N, C, H, W, KL, KS, _lib.dtype_code(x.dtype),
+                                             ws.data_ptr(), ws.numel(), _lib.current_stream_ptr())
+    _lib.check(rc, "slak_lk_branches_bwd_filter")
+    _count(4)
+    return dw1, dw2, dw3

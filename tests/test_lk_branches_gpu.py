@@ -44,3 +44,37 @@ def test_headline_shape_uses_tensor_cores_and_matches_cuda_core_path():
         # same bf16 operands, fp32 accumulation in both: only summation order differs
         d = (y.float() - y_simt.float()).abs().max().item()
         assert d <= 2.0 ** -7 * y_simt.float().abs().max().item(), d
+
+
+TC_CASES = [(2, 3, 56, 56, 51), (5, 4, 56, 56, 51), (1, 2, 56, 56, 61), (3, 2, 48, 48, 51), (4, 3, 24, 24, 49),
+            (3, 5, 40, 56, 31), (7, 2, 16, 8, 13), (2, 2, 56, 56, 5), (33, 2, 56, 56, 51)]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_fused_backward_data_and_filter_match_oracle(case):
+    N, C, H, W, KL = case
+    g = torch.Generator().manual_seed(99 + KL + N)
+    x = torch.randn(N, C, H, W, generator=g).bfloat16()
+    dys = [torch.randn(N, C, H, W, generator=g).bfloat16() for _ in range(3)]
+    ws = [torch.randn(C, 1, *k, generator=g) * 0.05 for k in ((KL, 5), (5, KL), (5, 5))]
+    assert ops.lk_branches_uses_tc(x.to(DEV), KL, 5)
+    dx64 = torch.zeros(N, C, H, W, dtype=torch.float64)
+    dw64 = []
+    for w, dy in zip(ws, dys):
+        dxi, dwi = orc.grads_torch(x.double(), orc.round_like(w, torch.bfloat16).double(), dy.double())
+        dx64 += dxi
+        dw64.append(dwi)
+    wd = [w.to(DEV) for w in ws]
+    dyd = [d.to(DEV) for d in dys]
+    dx = ops.lk_branches_backward_data(*dyd, *wd).cpu().double()
+    err = (dx - dx64).abs().max().item() / dx64.abs().max().item()
+    # two bf16 roundings (the 5x5 branch is rounded once before the final sum)
+    assert err <= 2.0 ** -7, err
+    dws = ops.lk_branches_backward_filter(x.to(DEV), *dyd, KL, 5)
+    for i, (dw, ref) in enumerate(zip(dws, dw64)):
+        assert dw.dtype == torch.float32 and tuple(dw.shape) == tuple(ref.shape)
+        e = (dw.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        assert e <= 1e-4, (i, e)
+    # deterministic (fixed-order reduction)
+    dws2 = ops.lk_branches_backward_filter(x.to(DEV), *dyd, KL, 5)
+    assert all(torch.equal(a, b) for a, b in zip(dws, dws2))
