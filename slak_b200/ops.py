@@ -234,3 +234,46 @@ def lk_branches_backward_filter(x, dy1, dy2, dy3, KL, KS):
     _lib.check(rc, "slak_lk_branches_bwd_filter")
     _count(4)
     return dw1, dw2, dw3
+
+
+class LKBranchesFunction(torch.autograd.Function):
+    """(y1, y2, y3) = the three depthwise branches of ReparamLargeKernelConv (models/SLaK.py:89-100) as one
+    autograd node: x is read once in forward; backward is the fused tensor-core dgrad/wgrad where the shape
+    allows, else the per-branch CUDA-core kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, w3):
+        x = x.contiguous()
+        w1, w2, w3 = w1.contiguous(), w2.contiguous(), w3.contiguous()
+        ctx.save_for_backward(x, w1, w2, w3)
+        return lk_branches_forward(x, w1, w2, w3)
+
+    @staticmethod
+    def backward(ctx, g1, g2, g3):
+        x, w1, w2, w3 = ctx.saved_tensors
+        g1, g2, g3 = g1.contiguous(), g2.contiguous(), g3.contiguous()
+        KL, KS = w1.size(2), w1.size(3)
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = any(ctx.needs_input_grad[1:])
+        dx = dw1 = dw2 = dw3 = None
+        if lk_branches_uses_tc(x, KL, KS):
+            if need_dx:
+                dx = lk_branches_backward_data(g1, g2, g3, w1, w2, w3)
+            if need_dw:
+                dw1, dw2, dw3 = lk_branches_backward_filter(x, g1, g2, g3, KL, KS)
+        else:
+            if need_dx:
+                dx = dwconv2d_backward_data(g1, w1)
+                dx += dwconv2d_backward_data(g2, w2)
+                dx += dwconv2d_backward_data(g3, w3)
+            if need_dw:
+                dw1 = dwconv2d_backward_filter(g1, x, w1)
+                dw2 = dwconv2d_backward_filter(g2, x, w2)
+                dw3 = dwconv2d_backward_filter(g3, x, w3)
+        return dx, dw1, dw2, dw3
+
+
+def lk_branches(x, w1, w2, w3):
+    if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise TypeError("Only support fp32, fp16 and bf16, get {}".format(x.dtype))
+    return LKBranchesFunction.apply(x, w1, w2, w3)

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .dwconv import DepthWiseConv2dImplicitGEMM
 
 use_sync_bn = True
@@ -131,10 +132,22 @@ class ReparamLargeKernelConv(nn.Module):
             out.append(self.small_conv)
         return out
 
+    def _fused_ok(self, x):
+        # the fused three-branch node needs the Decom layout with a small branch, no conv bias, fp32 taps
+        return (self.Decom and hasattr(self, "small_conv") and x.is_cuda and x.dim() == 4 and
+                x.dtype in (torch.float32, torch.float16, torch.bfloat16) and
+                self.LoRA1.conv.bias is None and self.LoRA1.conv.weight.dtype == torch.float32)
+
     def forward(self, inputs):
         if hasattr(self, "lkb_reparam"):
             return self.lkb_reparam(inputs)
-        outs = [b(inputs) for b in self.branches()]
+        if self._fused_ok(inputs):
+            # one node for the three convolutions (x read once; tensor cores where the shape allows),
+            # then the reference's per-branch BN and sum (models/SLaK.py:93-95)
+            ys = ops.lk_branches(inputs, self.LoRA1.conv.weight, self.LoRA2.conv.weight, self.small_conv.conv.weight)
+            outs = [b.bn(y) if hasattr(b, "bn") else y for b, y in zip((self.LoRA1, self.LoRA2, self.small_conv), ys)]
+        else:
+            outs = [b(inputs) for b in self.branches()]
         out = outs[0]
         for o in outs[1:]:
             out = out + o
