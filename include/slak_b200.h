@@ -110,6 +110,7 @@ SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w
  *               scratch tensor of the size of dx (holds the 5x5 branch between the two launches).
  *   bwd_filter: dw1 [C,1,KL,KS], dw2 [C,1,KS,KL], dw3 [C,1,KS,KS] in fp32, deterministic;
  *               workspace of slak_lk_branches_bwd_filter_workspace() bytes. */
+SLAK_API int slak_lk_branches_bwd_uses_tc(int N, int C, int H, int W, int KL, int KS, int dtype);
 SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const void* dy3,
                                        const float* w1, const float* w2, const float* w3,
                                        void* dx, void* tmp, int N, int C, int H, int W,

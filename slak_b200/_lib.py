@@ -33,6 +33,7 @@ SIGNATURES = {
     "slak_dwconv2d_bwd_filter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "slak_lk_branches_uses_tc": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "slak_lk_branches_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "slak_lk_branches_bwd_uses_tc": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "slak_lk_branches_bwd_data": (_i, [_vp] * 8 + [_i] * 7 + [_vp]),
     "slak_lk_branches_bwd_filter_workspace": (_sz, [_i] * 6),
     "slak_lk_branches_bwd_filter": (_i, [_vp] * 7 + [_i] * 7 + [_vp, _sz, _vp]),

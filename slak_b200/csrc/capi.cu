@@ -23,6 +23,7 @@ int dwconv_simt_wgrad(const void* dy, const void* x, float* dw, int N, int C, in
 // dwconv_tc_fwd.cu
 namespace tc {
 bool lk3_tc_supported(int N, int C, int H, int W, int KL);
+bool lk3_bwd_tc_supported(int N, int C, int H, int W, int KL);
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
                int N, int C, int H, int W, int KL, cudaStream_t st);
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
@@ -126,13 +127,17 @@ SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w
   return dwconv_simt_fwd(x, w3, y3, N, C, H, W, KS, KS, dtype, SLAK_F32, 0, st);
 }
 
+SLAK_API int slak_lk_branches_bwd_uses_tc(int N, int C, int H, int W, int KL, int KS, int dtype) {
+  return (dtype == SLAK_BF16 && KS == 5 && N > 0 && C > 0 && tc::lk3_bwd_tc_supported(N, C, H, W, KL)) ? 1 : 0;
+}
+
 SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const void* dy3, const float* w1,
                                        const float* w2, const float* w3, void* dx, void* tmp, int N, int C,
                                        int H, int W, int KL, int KS, int dtype, void* stream) {
   int rc = check_conv_args(dy1, w1, dx, N, C, H, W, KL, KS, dtype, SLAK_F32);
   if (rc) return rc;
   SLAK_REQUIRE(dy2 && dy3 && w2 && w3 && tmp, SLAK_ERR_BAD_ARG, "null tensor pointer");
-  SLAK_REQUIRE(slak_lk_branches_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
+  SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
                "fused bwd_data covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
   cudaStream_t st = (cudaStream_t)stream;
   rc = tc::lk_conv_tc(nullptr, nullptr, dy3, w3, nullptr, tmp, N, C, H, W, KL, KS, /*flip=*/1, st);
@@ -152,7 +157,7 @@ SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const v
   int rc = check_conv_args(x, dy1, dw1, N, C, H, W, KL, KS, dtype, dtype);
   if (rc) return rc;
   SLAK_REQUIRE(dy2 && dy3 && dw2 && dw3, SLAK_ERR_BAD_ARG, "null tensor pointer");
-  SLAK_REQUIRE(slak_lk_branches_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
+  SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
                "fused bwd_filter covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
   const size_t need = tc::lk3_wgrad_tc_workspace(N, C, KL);
   SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE, "bwd_filter workspace too small: %zu < %zu",

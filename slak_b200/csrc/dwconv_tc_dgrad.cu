@@ -333,3 +333,12 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
 
 }  // namespace tc
 }  // namespace slak
+
+namespace slak { namespace tc {
+// shapes covered by the tensor-core dgrad/wgrad kernels (64-class planes staged by TMA)
+bool lk3_bwd_tc_supported(int N, int C, int H, int W, int KL) {
+  (void)N; (void)C;
+  const TcShape s = tc_shape(H, W);
+  return s.tile == 64 && s.tma && H >= 8 && W >= 8 && (KL & 1) && KL >= 5 && KL * 5 * 2 + 25 <= 4000;
+}
+} }

@@ -6,66 +6,94 @@
 // Formulation (banded-Toeplitz GEMMs, per channel):
 //   long axis of a branch  -> contraction (K) against a Toeplitz matrix of the taps, built in
 //                             shared memory once per CTA (B operand, K-major, SWIZZLE_128B)
-//   short axis (5 taps)    -> five accumulating MMAs whose A operand (the image plane) starts
+//   short axis (5 taps)    -> five accumulating MMAs whose A operand (the image planes) starts
 //                             (t-2) ROWS later: a row shift is a +128-byte descriptor offset
-//   y2|y3 [(plane,p), q]  += X [(plane,p+r-2), w]   * [T2_r ; T3_r][q, w]    M=128 N=128 K=64
-//   y1^T  [(plane,q), p]  += X^T[(plane,q+s-2), h]  * T1_s[p, h]             M=128 N=64  K=64
-//   M stacks two planes of the same channel; each 64x64 plane tile is zero beyond 56 rows, so
-//   the zero rows double as the "same" padding between the two stacked planes.
-//   X comes from one TMA load per plane (OOB zero fill = padding); X^T is made in shared memory
-//   with ldmatrix.trans/stmatrix by two warps.
+//   y2|y3 [(plane,p), q]  += X [(plane,p+r-2), w]   * [T2_r ; T3_r][q, w]    M=128 N=2T K=T
+//   y1^T  [(plane,q), p]  += X^T[(plane,q+s-2), h]  * T1_s[p, h]             M=128 N=T  K=T
+//   A plane occupies a T x T tile (T = 64, 32 or 16 >= H+2, W+2) that is zero beyond H x W; M=128
+//   stacks 128/T planes of the same channel and the zero rows double as the "same" padding
+//   between stacked planes.
+//   X is staged by TMA (T=64, W%8==0: 3-D tiled map, OOB zero fill) or by cp.async pieces; X^T is
+//   made in shared memory with ldmatrix.trans/stmatrix.
 //
-// Warp roles (256 threads): w0 TMA producer | w1 MMA issuer | w2-3 transposers (w2 owns TMEM
-// alloc) | w4-7 epilogue (TMEM -> registers -> bf16 -> global; y1 is transposed back through smem).
+// Warp roles (320 threads): w0 loader | w1 MMA issuer | w2-3 transposers (w2 owns TMEM alloc) |
+// w4-7 epilogue (TMEM -> registers -> bf16 -> global; y1 is transposed back through smem) |
+// w8-9 extra loaders (cp.async path only).
 #include "common.cuh"
 #include "tc_common.cuh"
-
-// How a SWIZZLE_128B K-major operand that starts on a 128-byte row which is not 1024-byte aligned
-// must be described (measured with tools/umma_probe.cu): base_offset field value.
-#ifndef SLAK_TC_BASE_OFF
-#define SLAK_TC_BASE_OFF(addr) 0u
-#endif
+#include <string.h>
 
 namespace slak {
 namespace tc {
 
 constexpr int kStages = 3;                       // X (natural) slots in flight
-constexpr int kTStages = 1;                      // X^T slots (refilled in the shadow of the b2|b3 MMAs)
 constexpr int kAccBufs = 2;
-constexpr int kPlaneBytes = 64 * 128;            // one 64x64 bf16 tile
-constexpr int kUnitBytes = 2 * kPlaneBytes;      // two stacked planes
+constexpr int kUnitBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kPad = 1024;                       // zero rows before/after a unit tile
-constexpr int kToep1Bytes = 5 * 64 * 128;        // 40 KB
-constexpr int kToep23Bytes = 5 * 128 * 128;      // 80 KB
 constexpr int kXSlot = kPad + kUnitBytes + kPad; // 18 KB
-constexpr int kOffToep1 = 0;
-constexpr int kOffToep23 = kOffToep1 + kToep1Bytes;
-constexpr int kOffXN = kOffToep23 + kToep23Bytes;
-constexpr int kOffXT = kOffXN + kStages * kXSlot;
-constexpr int kOffY1 = kOffXT + kTStages * kXSlot;         // 16 KB staging for the y1 transpose
-constexpr int kOffBar = kOffY1 + kUnitBytes;
-constexpr int kSmemBytes = kOffBar + 256 + 1024;           // + alignment slack
-constexpr int kTmemCols = 512;
-constexpr int kAccCols = 192;                               // D1T: 64 cols, D23: 128 cols
 constexpr int kNumTransposerWarps = 2;
+constexpr int kThreads = 320;
+
+template <int T> struct FwdCfg {
+  static constexpr int PPU = 128 / T;            // planes per unit
+  static constexpr int KSTEPS = T / 16;
+  static constexpr int kToep1 = 5 * T * 128;
+  static constexpr int kToep23 = 5 * 2 * T * 128;
+  static constexpr int kOffToep1 = 0;
+  static constexpr int kOffToep23 = kToep1;
+  static constexpr int kOffXN = kOffToep23 + kToep23;
+  static constexpr int kOffXT = kOffXN + kStages * kXSlot;
+  static constexpr int kOffY1 = kOffXT + kXSlot;
+  static constexpr int kOffBar = kOffY1 + kUnitBytes;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kAccCols = 3 * T;
+  static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
+};
 
 struct FwdParams {
+  const __nv_bfloat16* x;
   const float* w1; const float* w2; const float* w3;       // fp32 taps [C,KL,5] [C,5,KL] [C,5,5]
   __nv_bfloat16* y1; __nv_bfloat16* y2; __nv_bfloat16* y3;
   int N, C, H, W, KL;
   int splits;            // CTAs per channel
-  int pairs_per_c;       // ceil(N/2)
+  int units_per_c;       // ceil(N / PPU)
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+// cp.async loader of one unit (PPU planes of channel c) into a SWIZZLE_128B K-major tile
+template <int T, int CB>
+__device__ __forceinline__ void load_unit_pieces(const __nv_bfloat16* __restrict__ x, uint32_t tile, int n0, int c,
+                                                 int N, int C, int H, int W, int lane) {
+  constexpr int PPU = 128 / T;
+  const int PR = (W * 2) / CB;               // pieces per row
+  const int per_plane = H * PR;
+  const size_t plane_bytes = (size_t)H * W * 2;
+  for (int pl = 0; pl < PPU; ++pl) {
+    const int n = n0 + pl;
+    if (n >= N) break;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + ((size_t)n * C + c) * plane_bytes;
+    for (int e = lane; e < per_plane; e += 32) {
+      const int p = e / PR, j = e - p * PR;
+      const int row = pl * T + p;
+      const int b = j * CB;
+      const uint32_t dst = tile + row * 128 + ((((b >> 4) ^ (row & 7))) << 4) + (b & 15);
+      const uint8_t* s = src + (size_t)p * W * 2 + b;
+      if constexpr (CB >= 4) {
+        cp_async<CB>(dst, s);
+      } else {
+        const uint16_t val = *reinterpret_cast<const uint16_t*>(s);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "h"(val) : "memory");
+      }
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256, 1)
+template <int T, int CB, bool TMA>
+__global__ void __launch_bounds__(kThreads, 1)
 lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
+  using Cfg = FwdCfg<T>;
+  constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2;
+  constexpr int kNumLoaders = TMA ? 1 : kStages;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned base (SWIZZLE_128B atoms)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
@@ -73,72 +101,65 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x / P.splits;
   const int split = blockIdx.x % P.splits;
-  const int u_begin = (int)(((long long)P.pairs_per_c * split) / P.splits);
-  const int u_end = (int)(((long long)P.pairs_per_c * (split + 1)) / P.splits);
+  const int u_begin = (int)(((long long)P.units_per_c * split) / P.splits);
+  const int u_end = (int)(((long long)P.units_per_c * (split + 1)) / P.splits);
+  const int n_units = u_end - u_begin;
   const int KL = P.KL, pad = KL / 2, H = P.H, W = P.W;
 
-  // barriers
-  constexpr int B_XN_FULL = 0, B_XN_EMPTY = kStages, B_XT_FULL = 2 * kStages, B_XT_EMPTY = B_XT_FULL + kTStages,
-                B_ACC_FULL = B_XT_EMPTY + kTStages, B_ACC_EMPTY = B_ACC_FULL + kAccBufs;
-  const uint32_t bar0 = base + kOffBar;
+  constexpr int B_XN_FULL = 0, B_XN_EMPTY = kStages, B_XT_FULL = 2 * kStages, B_XT_EMPTY = B_XT_FULL + 1,
+                B_ACC_FULL = B_XT_EMPTY + 1, B_ACC_EMPTY = B_ACC_FULL + kAccBufs;
+  const uint32_t bar0 = base + Cfg::kOffBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cfg::kOffBar + 192);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(BAR(B_XN_FULL + s), 1);                          // TMA expect_tx arrive
+      mbar_init(BAR(B_XN_FULL + s), 1);                          // TMA expect_tx arrive / loader lane 0
       mbar_init(BAR(B_XN_EMPTY + s), 1 + kNumTransposerWarps);   // MMA commit + transposers done reading
     }
-    for (int s = 0; s < kTStages; ++s) {
-      mbar_init(BAR(B_XT_FULL + s), kNumTransposerWarps);        // transposers wrote X^T
-      mbar_init(BAR(B_XT_EMPTY + s), 1);                         // MMA commit
-    }
+    mbar_init(BAR(B_XT_FULL), kNumTransposerWarps);              // transposers wrote X^T
+    mbar_init(BAR(B_XT_EMPTY), 1);                               // MMA commit
     for (int a = 0; a < kAccBufs; ++a) {
       mbar_init(BAR(B_ACC_FULL + a), 1);                         // MMA commit
       mbar_init(BAR(B_ACC_EMPTY + a), 4);                        // one arrival per epilogue warp
     }
     mbar_fence_init();
-    tma_prefetch_desc(&xmap);
+    if (TMA) tma_prefetch_desc(&xmap);
   }
 
-  // ---- zero the pads of the X / X^T slots and build the Toeplitz operands (all threads) -------
+  // ---- zero the X / X^T slots (pads + tile padding stay zero forever) and build the Toeplitz operands ----
   {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    for (int s = 0; s < kStages + kTStages; ++s) {
-      uint8_t* slot = sm + kOffXN + s * kXSlot;
-      for (int i = tid; i < kPad / 16; i += 256) {
-        reinterpret_cast<uint4*>(slot)[i] = z;
-        reinterpret_cast<uint4*>(slot + kPad + kUnitBytes)[i] = z;
-      }
-    }
-    // taps of channel c, rounded to bf16, staged as fp32 in the y1 staging area
-    float* wst = reinterpret_cast<float*>(sm + kOffY1);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (kStages + 1) * kXSlot / 16; i += kThreads)
+      reinterpret_cast<uint4*>(sm + Cfg::kOffXN)[i] = z;
+    float* wst = reinterpret_cast<float*>(sm + Cfg::kOffY1);
     float* w1s = wst;                 // [KL][5]
     float* w2s = wst + KL * 5;        // [5][KL]
     float* w3s = wst + 2 * KL * 5;    // [5][5]
-    for (int i = tid; i < KL * 5; i += 256) {
+    for (int i = tid; i < KL * 5; i += kThreads) {
       w1s[i] = P.w1[(size_t)c * KL * 5 + i];
       w2s[i] = P.w2[(size_t)c * KL * 5 + i];
     }
     if (tid < 25) w3s[tid] = P.w3[(size_t)c * 25 + tid];
     __syncthreads();
+    constexpr int CH = T / 8;         // 16-byte chunks per row that are ever read
     // T1_s[p][h] = w1[h-p+pad][s]
-    for (int ch = tid; ch < 5 * 64 * 8; ch += 256) {
-      const int s = ch / 512, rem = ch - s * 512, p = rem >> 3, k8 = rem & 7;
+    for (int ch = tid; ch < 5 * T * CH; ch += kThreads) {
+      const int s = ch / (T * CH), rem = ch - s * (T * CH), p = rem / CH, k8 = rem - p * CH;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int t = (k8 * 8 + j) - p + pad;
         v[j] = (t >= 0 && t < KL) ? w1s[t * 5 + s] : 0.f;
       }
-      uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-      *reinterpret_cast<uint4*>(sm + kOffToep1 + s * (64 * 128) + p * 128 + ((k8 ^ (p & 7)) << 4)) = q;
+      *reinterpret_cast<uint4*>(sm + Cfg::kOffToep1 + s * (T * 128) + p * 128 + ((k8 ^ (p & 7)) << 4)) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
-    // T23_r rows 0..63: T2_r[q][w] = w2[r][w-q+pad] ; rows 64..127: T3_r[q][w] = w3[r][w-q+2]
-    for (int ch = tid; ch < 5 * 128 * 8; ch += 256) {
-      const int r = ch / 1024, rem = ch - r * 1024, row = rem >> 3, k8 = rem & 7;
+    // T23_r rows 0..T-1: T2_r[q][w] = w2[r][w-q+pad] ; rows T..2T-1: T3_r[q][w] = w3[r][w-q+2]
+    for (int ch = tid; ch < 5 * 2 * T * CH; ch += kThreads) {
+      const int r = ch / (2 * T * CH), rem = ch - r * (2 * T * CH), row = rem / CH, k8 = rem - row * CH;
       float v[8];
-      if (row < 64) {
+      if (row < T) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int t = (k8 * 8 + j) - row + pad;
@@ -147,73 +168,87 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int t = (k8 * 8 + j) - (row - 64) + 2;
+          const int t = (k8 * 8 + j) - (row - T) + 2;
           v[j] = (t >= 0 && t < 5) ? w3s[r * 5 + t] : 0.f;
         }
       }
-      uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-      *reinterpret_cast<uint4*>(sm + kOffToep23 + r * (128 * 128) + row * 128 + ((k8 ^ (row & 7)) << 4)) = q;
+      *reinterpret_cast<uint4*>(sm + Cfg::kOffToep23 + r * (2 * T * 128) + row * 128 + ((k8 ^ (row & 7)) << 4)) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
   }
   fence_proxy_async();      // generic-proxy writes above are read by the tensor core (async proxy)
-  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int n_units = u_end - u_begin;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (elect_one()) {
-      for (int i = 0; i < n_units; ++i) {
-        const int st = i % kStages, ph = (i / kStages) & 1;
+  const bool is_loader = (warp == 0) || (!TMA && warp >= 8);
+  if (is_loader) {
+    if constexpr (TMA) {
+      // ================= TMA producer (T = 64: two planes per unit) =================
+      if (elect_one()) {
+        for (int i = 0; i < n_units; ++i) {
+          const int st = i % kStages, ph = (i / kStages) & 1;
+          mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
+          const int n0 = PPU * (u_begin + i);
+          const uint32_t dst = base + Cfg::kOffXN + st * kXSlot + kPad;
+          mbar_expect_tx(BAR(B_XN_FULL + st), kUnitBytes);
+#pragma unroll
+          for (int pl = 0; pl < PPU; ++pl)
+            tma_load_3d(dst + pl * (T * 128), &xmap, BAR(B_XN_FULL + st), 0, 0, min(n0 + pl, P.N - 1) * P.C + c);
+        }
+      }
+    } else {
+      // ================= cp.async loaders: loader j owns stage j, one unit in flight each =============
+      const int lj = (warp == 0) ? 0 : (warp - 7);           // 0, 1, 2
+      for (int i = lj; i < n_units; i += kNumLoaders) {
+        const int st = lj;                                    // == i % kStages
+        const int ph = (i / kStages) & 1;
         mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
-        const int n0 = 2 * (u_begin + i);
-        const uint32_t dst = base + kOffXN + st * kXSlot + kPad;
-        mbar_expect_tx(BAR(B_XN_FULL + st), kUnitBytes);
-        const int na = n0, nb = min(n0 + 1, P.N - 1);
-        tma_load_3d(dst, &xmap, BAR(B_XN_FULL + st), 0, 0, na * P.C + c);
-        tma_load_3d(dst + kPlaneBytes, &xmap, BAR(B_XN_FULL + st), 0, 0, nb * P.C + c);
+        load_unit_pieces<T, CB>(P.x, base + Cfg::kOffXN + st * kXSlot + kPad, PPU * (u_begin + i), c, P.N, P.C, H, W, lane);
+        cp_async_commit();
+        cp_async_wait_all();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_XN_FULL + st));
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (elect_one()) {
-      constexpr uint32_t idesc23 = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc23 = umma_idesc_bf16(128, 2 * T);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, T);
       for (int i = 0; i < n_units; ++i) {
         const int st = i % kStages, ph = (i / kStages) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
-        const int ts = i % kTStages, tph = (i / kTStages) & 1;
         mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);   // epilogue drained this accumulator buffer
         mbar_wait(BAR(B_XN_FULL + st), ph);          // X landed
         tc_fence_after();
-        const uint32_t xn = base + kOffXN + st * kXSlot + kPad;
-        const uint32_t xt = base + kOffXT + ts * kXSlot + kPad;
-        const uint32_t d1 = tmem + ab * kAccCols;
-        const uint32_t d23 = d1 + 64;
+        const uint32_t xn = base + Cfg::kOffXN + st * kXSlot + kPad;
+        const uint32_t xt = base + Cfg::kOffXT + kPad;
+        const uint32_t d1 = tmem + ab * Cfg::kAccCols;
+        const uint32_t d23 = d1 + T;
 #pragma unroll
         for (int r = 0; r < 5; ++r)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < KSTEPS; ++k) {
             const uint32_t a = xn + (r - 2) * 128 + k * 32;
-            const uint32_t b = base + kOffToep23 + r * (128 * 128) + k * 32;
-            umma_bf16(d23, umma_desc_k_sw128(a, SLAK_TC_BASE_OFF(a)), umma_desc_k_sw128(b, 0), idesc23, (r | k) != 0);
+            const uint32_t b = base + Cfg::kOffToep23 + r * (2 * T * 128) + k * 32;
+            umma_bf16(d23, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc23, (r | k) != 0);
           }
         umma_commit(BAR(B_XN_EMPTY + st));           // X slot free (with the transposers' arrivals)
-        mbar_wait(BAR(B_XT_FULL + ts), tph);         // X^T written
+        mbar_wait(BAR(B_XT_FULL), i & 1);            // X^T written
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 5; ++s)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < KSTEPS; ++k) {
             const uint32_t a = xt + (s - 2) * 128 + k * 32;
-            const uint32_t b = base + kOffToep1 + s * (64 * 128) + k * 32;
-            umma_bf16(d1, umma_desc_k_sw128(a, SLAK_TC_BASE_OFF(a)), umma_desc_k_sw128(b, 0), idesc1, (s | k) != 0);
+            const uint32_t b = base + Cfg::kOffToep1 + s * (T * 128) + k * 32;
+            umma_bf16(d1, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc1, (s | k) != 0);
           }
-        umma_commit(BAR(B_XT_EMPTY + ts));           // X^T slot free
+        umma_commit(BAR(B_XT_EMPTY));                // X^T slot free
         umma_commit(BAR(B_ACC_FULL + ab));           // accumulators ready
       }
     }
@@ -221,18 +256,20 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     // ================= transposers: X (natural) -> X^T, 8x8 blocks =================
     const int tw = warp - 2;
     const int m = lane >> 3, kk = lane & 7;     // matrix id within the x4, row within the 8x8 block
+    constexpr int NB = T / 8;                   // blocks per plane edge
     for (int i = 0; i < n_units; ++i) {
       const int st = i % kStages, ph = (i / kStages) & 1;
-      const int ts = i % kTStages, tph = (i / kTStages) & 1;
       mbar_wait(BAR(B_XN_FULL + st), ph);       // X landed
-      mbar_wait(BAR(B_XT_EMPTY + ts), tph ^ 1); // previous X^T of this slot consumed
-      const uint32_t xn = base + kOffXN + st * kXSlot + kPad;
-      const uint32_t xt = base + kOffXT + ts * kXSlot + kPad;
-      for (int it = tw; it < 32; it += kNumTransposerWarps) {
-        const int h = it >> 4, bi = (it >> 1) & 7, g = it & 1;
-        const int bj = 4 * g + m;
-        const uint32_t src = xn + (64 * h + 8 * bi + kk) * 128 + ((bj ^ kk) << 4);
-        const uint32_t dst = xt + (64 * h + 8 * bj + kk) * 128 + ((bi ^ kk) << 4);
+      mbar_wait(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed
+      const uint32_t xn = base + Cfg::kOffXN + st * kXSlot + kPad;
+      const uint32_t xt = base + Cfg::kOffXT + kPad;
+#pragma unroll 4
+      for (int it = tw; it < T / 2; it += kNumTransposerWarps) {
+        const int blk = 4 * it + m;
+        const int pl = blk / (NB * NB), rem = blk - pl * (NB * NB);
+        const int bi = rem / NB, bj = rem - bi * NB;
+        const uint32_t src = xn + (pl * T + 8 * bi + kk) * 128 + ((bj ^ kk) << 4);
+        const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + ((bi ^ kk) << 4);
         uint32_t r0, r1, r2, r3;
         ldmatrix_x4_trans(src, r0, r1, r2, r3);
         stmatrix_x4(dst, r0, r1, r2, r3);
@@ -240,67 +277,61 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(BAR(B_XT_FULL + ts));       // X^T ready
+        mbar_arrive(BAR(B_XT_FULL));            // X^T ready
         mbar_arrive(BAR(B_XN_EMPTY + st));      // done reading X
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ================= epilogue =================
     const int e = warp - 4;
-    const int L = e * 32 + lane;                // TMEM lane = (plane half, row)
-    const int half = L >> 6, row = L & 63;
+    const int L = e * 32 + lane;                // TMEM lane = (plane in unit, row)
+    const int pl = L / T, row = L % T;
     const size_t plane_elems = (size_t)H * W;
-    uint8_t* y1s = sm + kOffY1;
-    const int wchunks = W >> 3;
+    uint8_t* y1s = sm + Cfg::kOffY1;
+    const int PR = W / E;                       // pieces per output row
     for (int i = 0; i < n_units; ++i) {
       const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
-      const int n = 2 * (u_begin + i) + half;
-      const bool plane_ok = n < P.N;
-      const size_t pbase = ((size_t)(plane_ok ? n : 0) * P.C + c) * plane_elems;
+      const int n = PPU * (u_begin + i) + pl;
+      const bool ok = (n < P.N) && (row < H);
+      const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
       mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
-      const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * kAccCols;
-      uint32_t v[64];
-      // ---- y2 (cols 64..127 of the buffer) and y3 (cols 128..191): natural orientation ----
+      const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * Cfg::kAccCols;
+      uint32_t v[T];
+      // ---- y2 (cols T..2T-1 of the buffer) and y3 (cols 2T..3T-1): natural orientation ----
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        tmem_ld32(t0 + 64 + br * 64, v);
-        tmem_ld32(t0 + 64 + br * 64 + 32, v + 32);
+        tmem_ld_cols<T>(t0 + T + br * T, v);
         tmem_ld_wait();
-        if (plane_ok && row < H) {
-          __nv_bfloat16* yo = (br == 0 ? P.y2 : P.y3) + pbase + (size_t)row * W;
+        if (ok) {
+          __nv_bfloat16* yo = (br == 0 ? P.y2 : P.y3) + rbase;
 #pragma unroll
-          for (int ck = 0; ck < 8; ++ck) {          // static register indices: no local-memory spill
-            if (ck < wchunks) {
-              uint4 o;
-              o.x = pack_bf16(__uint_as_float(v[8 * ck + 0]), __uint_as_float(v[8 * ck + 1]));
-              o.y = pack_bf16(__uint_as_float(v[8 * ck + 2]), __uint_as_float(v[8 * ck + 3]));
-              o.z = pack_bf16(__uint_as_float(v[8 * ck + 4]), __uint_as_float(v[8 * ck + 5]));
-              o.w = pack_bf16(__uint_as_float(v[8 * ck + 6]), __uint_as_float(v[8 * ck + 7]));
-              *reinterpret_cast<uint4*>(yo + 8 * ck) = o;
-            }
-          }
+          for (int j = 0; j < T / E; ++j)          // static register indices
+            if (j < PR) store_bf16_piece<E>(yo + j * E, v + j * E);
         }
       }
-      // ---- y1^T (cols 0..63): this thread holds column `row`(=q) for p = 0..63 -> staging[p][q] ----
-      tmem_ld32(t0, v);
-      tmem_ld32(t0 + 32, v + 32);
+      // ---- y1^T (cols 0..T-1): this thread holds column `row`(=q) for p = 0..T-1 -> staging[(pl,p)][q] ----
+      tmem_ld_cols<T>(t0, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));  // accumulators drained
+      if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));   // accumulators drained
 #pragma unroll
-      for (int p = 0; p < 64; ++p) {
-        const uint32_t off = (uint32_t)(half * 64 + p) * 128 + ((((uint32_t)row >> 3) ^ (p & 7)) << 4) + (row & 7) * 2;
+      for (int p = 0; p < T; ++p) {
+        const uint32_t r = (uint32_t)(pl * T + p);
+        const uint32_t off = r * 128 + ((((uint32_t)row >> 3) ^ (r & 7)) << 4) + (row & 7) * 2;
         *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(v[p]));
       }
       named_bar_sync(1, 128);
-      if (plane_ok && row < H) {
-        __nv_bfloat16* yo = P.y1 + pbase + (size_t)row * W;
-        for (int ck = 0; ck < wchunks; ++ck) {
-          const uint32_t off = (uint32_t)(half * 64 + row) * 128 + ((ck ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(yo + 8 * ck) = *reinterpret_cast<const uint4*>(y1s + off);
-        }
+      if (ok) {
+        __nv_bfloat16* yo = P.y1 + rbase;
+        const uint32_t r = (uint32_t)(pl * T + row);
+#pragma unroll
+        for (int j = 0; j < T / E; ++j)
+          if (j < PR) {
+            const uint32_t b = j * CB;
+            copy_piece<E>(yo + j * E, y1s + r * 128 + (((b >> 4) ^ (r & 7)) << 4) + (b & 15));
+          }
       }
       named_bar_sync(1, 128);                     // staging free for the next unit
     }
@@ -308,7 +339,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem);
 }
 
 // ---- host side --------------------------------------------------------------------------
@@ -343,40 +374,79 @@ int make_plane_map(CUtensorMap* map, const void* x, int N, int C, int H, int W) 
   return SLAK_OK;
 }
 
+// Tile class and piece size for a plane shape; tile 0 = not covered by the tensor-core kernels.
+TcShape tc_shape(int H, int W) {
+  TcShape s{0, 0, false};
+  const int m = H > W ? H : W;
+  if (H < 1 || W < 1 || m > 62) return s;
+  s.tile = m <= 14 ? 16 : (m <= 30 ? 32 : 64);
+  const int rb = W * 2;
+  s.cb = (rb % 16 == 0) ? 16 : (rb % 8 == 0) ? 8 : (rb % 4 == 0) ? 4 : 2;
+  if (s.tile == 64) {
+    s.tma = (s.cb == 16);
+    if (!s.tma) s.tile = 0;          // 64-class planes go through TMA only
+  } else {
+    if (s.cb == 16) s.cb = 8;        // instantiated piece sizes for the small classes: 8 / 4 / 2 bytes
+    if (s.tile == 16 && s.cb == 8) s.cb = 4;
+  }
+  return s;
+}
+
 bool lk3_tc_supported(int N, int C, int H, int W, int KL) {
   (void)N; (void)C;
-  return H >= 8 && W >= 8 && H <= 62 && W <= 62 && (W % 8) == 0 && (KL & 1) && KL >= 5 && KL * 5 * 2 + 25 <= 4000;
+  return tc_shape(H, W).tile != 0 && (KL & 1) && KL >= 5 && KL * 5 * 2 + 25 <= 4000;
+}
+
+int tc_pick_splits(int C, int units) {
+  const int sms = sm_count();
+  int best = 1; double best_eff = 0.0;
+  const int max_s = units >= 8 ? units / 4 : 1;
+  for (int s = 1; s <= max_s && s <= 64; ++s) {
+    const long long ctas = (long long)C * s;
+    const long long waves = (ctas + sms - 1) / sms;
+    const int per = (units + s - 1) / s;
+    const double eff = (double)C * units / ((double)waves * sms * per) * (per / (per + 1.5));
+    if (eff > best_eff) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+template <int T, int CB, bool TMA>
+static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
+  using Cfg = FwdCfg<T>;
+  P.units_per_c = (P.N + Cfg::PPU - 1) / Cfg::PPU;
+  P.splits = tc_pick_splits(P.C, P.units_per_c);
+  auto kern = lk3_fwd_tc_kernel<T, CB, TMA>;
+  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  kern<<<P.C * P.splits, kThreads, Cfg::kSmem, st>>>(map, P);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
 }
 
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
                int N, int C, int H, int W, int KL, cudaStream_t st) {
-  SLAK_REQUIRE(lk3_tc_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED,
-               "tensor-core path needs 8 <= H,W <= 62, W %% 8 == 0 (got %dx%d)", H, W);
+  SLAK_REQUIRE(lk3_tc_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   SLAK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SLAK_ERR_BAD_ARG, "x must be 16-byte aligned");
+  const TcShape s = tc_shape(H, W);
   CUtensorMap map;
-  int rc = make_plane_map(&map, x, N, C, H, W);
-  if (rc) return rc;
+  memset(&map, 0, sizeof(map));
+  if (s.tma) {
+    int rc = make_plane_map(&map, x, N, C, H, W);
+    if (rc) return rc;
+  }
   FwdParams P;
+  P.x = (const __nv_bfloat16*)x;
   P.w1 = w1; P.w2 = w2; P.w3 = w3;
   P.y1 = (__nv_bfloat16*)y1; P.y2 = (__nv_bfloat16*)y2; P.y3 = (__nv_bfloat16*)y3;
   P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL;
-  P.pairs_per_c = (N + 1) / 2;
-  // CTAs per channel: fill the SMs with whole waves, at least ~8 plane pairs per CTA
-  const int sms = sm_count();
-  int best = 1; double best_eff = 0.0;
-  const int max_s = P.pairs_per_c >= 8 ? P.pairs_per_c / 8 : 1;
-  for (int s = 1; s <= max_s && s <= 64; ++s) {
-    const long long ctas = (long long)C * s;
-    const long long waves = (ctas + sms - 1) / sms;
-    const int per = (P.pairs_per_c + s - 1) / s;
-    const double eff = (double)C * P.pairs_per_c / ((double)waves * sms * per) * (per / (per + 1.5));
-    if (eff > best_eff) { best_eff = eff; best = s; }
+  if (s.tile == 64) return launch_fwd<64, 16, true>(map, P, st);
+  if (s.tile == 32) {
+    if (s.cb == 8) return launch_fwd<32, 8, false>(map, P, st);
+    if (s.cb == 4) return launch_fwd<32, 4, false>(map, P, st);
+    return launch_fwd<32, 2, false>(map, P, st);
   }
-  P.splits = best;
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(lk3_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  lk3_fwd_tc_kernel<<<C * P.splits, 256, kSmemBytes, st>>>(map, P);
-  SLAK_CUDA_TRY(cudaGetLastError());
-  return SLAK_OK;
+  if (s.cb == 4) return launch_fwd<16, 4, false>(map, P, st);
+  return launch_fwd<16, 2, false>(map, P, st);
 }
 
 }  // namespace tc

@@ -115,3 +115,86 @@ __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t
 
 }  // namespace tc
 }  // namespace slak
+
+// ---- additions: cp.async pieces, 16-column TMEM load, tile-class descriptor -------------------
+namespace slak {
+namespace tc {
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+
+// plane tile class chosen for an H x W plane: tile edge (64/32/16, 0 = unsupported), global piece
+// size in bytes for loads/stores, and whether the TMA tiled path applies
+struct TcShape { int tile; int cb; bool tma; };
+TcShape tc_shape(int H, int W);
+int tc_pick_splits(int C, int units);
+
+// ---- epilogue helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// E consecutive fp32 values (raw bits) -> bf16 -> one store of 2*E bytes
+template <int E>
+__device__ __forceinline__ void store_bf16_piece(__nv_bfloat16* dst, const uint32_t* v) {
+  if constexpr (E == 8) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])),
+                                                pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                                                pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])),
+                                                pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
+  } else if constexpr (E == 4) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])),
+                                                pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])));
+  } else if constexpr (E == 2) {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  } else {
+    *dst = __float2bfloat16_rn(__uint_as_float(v[0]));
+  }
+}
+// E bf16 values read from global (2*E bytes) added to fp32 values held as raw bits
+template <int E>
+__device__ __forceinline__ void add_bf16_piece(uint32_t* v, const __nv_bfloat16* src) {
+  if constexpr (E >= 2) {
+    uint32_t raw[E / 2];
+    if constexpr (E == 8) { const uint4 t = *reinterpret_cast<const uint4*>(src); raw[0] = t.x; raw[1] = t.y; raw[2] = t.z; raw[3] = t.w; }
+    else if constexpr (E == 4) { const uint2 t = *reinterpret_cast<const uint2*>(src); raw[0] = t.x; raw[1] = t.y; }
+    else { raw[0] = *reinterpret_cast<const uint32_t*>(src); }
+#pragma unroll
+    for (int j = 0; j < E / 2; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[j]));
+      v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + f.x);
+      v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + f.y);
+    }
+  } else {
+    v[0] = __float_as_uint(__uint_as_float(v[0]) + __bfloat162float(*src));
+  }
+}
+template <int E>
+__device__ __forceinline__ void copy_piece(__nv_bfloat16* dst, const uint8_t* src) {
+  if constexpr (E == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+  else if constexpr (E == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+  else if constexpr (E == 2) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+  else *dst = *reinterpret_cast<const __nv_bfloat16*>(src);
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  if constexpr (NC == 64) { tmem_ld32(taddr, v); tmem_ld32(taddr + 32, v + 32); }
+  else if constexpr (NC == 32) { tmem_ld32(taddr, v); }
+  else { tmem_ld16(taddr, v); }
+}
+
+}  // namespace tc
+}  // namespace slak

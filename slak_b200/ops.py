@@ -169,6 +169,11 @@ def lk_branches_uses_tc(x: torch.Tensor, KL: int, KS: int) -> bool:
     return bool(_lib.load().slak_lk_branches_uses_tc(N, C, H, W, KL, KS, _lib.dtype_code(x.dtype)))
 
 
+def lk_branches_bwd_uses_tc(x: torch.Tensor, KL: int, KS: int) -> bool:
+    N, C, H, W = x.shape
+    return bool(_lib.load().slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, _lib.dtype_code(x.dtype)))
+
+
 def lk_branches_forward(x, w1, w2, w3=None):
     """(y1, y2, y3) = (dwconv_{KLxKS}, dwconv_{KSxKL}, dwconv_{KSxKS})(x) with the fp32 Parameters
     w1 [C,1,KL,KS], w2 [C,1,KS,KL], w3 [C,1,KS,KS] (or None).  One tcgen05 kernel when the shape
@@ -256,7 +261,7 @@ class LKBranchesFunction(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_dw = any(ctx.needs_input_grad[1:])
         dx = dw1 = dw2 = dw3 = None
-        if lk_branches_uses_tc(x, KL, KS):
+        if lk_branches_bwd_uses_tc(x, KL, KS):
             if need_dx:
                 dx = lk_branches_backward_data(g1, g2, g3, w1, w2, w3)
             if need_dw:

@@ -57,7 +57,7 @@ def test_fused_backward_data_and_filter_match_oracle(case):
     x = torch.randn(N, C, H, W, generator=g).bfloat16()
     dys = [torch.randn(N, C, H, W, generator=g).bfloat16() for _ in range(3)]
     ws = [torch.randn(C, 1, *k, generator=g) * 0.05 for k in ((KL, 5), (5, KL), (5, 5))]
-    assert ops.lk_branches_uses_tc(x.to(DEV), KL, 5)
+    assert ops.lk_branches_bwd_uses_tc(x.to(DEV), KL, 5)
     dx64 = torch.zeros(N, C, H, W, dtype=torch.float64)
     dw64 = []
     for w, dy in zip(ws, dys):

@@ -47,10 +47,11 @@ def test_mask_apply_multi_tensor_ieee_semantics():
     ed[1] = None
     lib = _lib.load()
     i64 = lambda v: torch.tensor(v, dtype=torch.int64, device="cuda")
-    rc = lib.slak_mask_apply(i64([t.data_ptr() for t in wd]).data_ptr(), i64([t.data_ptr() for t in md]).data_ptr(),
-                             i64([t.data_ptr() if t is not None else 0 for t in ed]).data_ptr(),
-                             i64([t.numel() for t in wd]).data_ptr(), len(wd), max(t.numel() for t in wd),
-                             torch.cuda.current_stream().cuda_stream)
+    tw, tm = i64([t.data_ptr() for t in wd]), i64([t.data_ptr() for t in md])      # tables must outlive the launch
+    te, tn = i64([t.data_ptr() if t is not None else 0 for t in ed]), i64([t.numel() for t in wd])
+    rc = lib.slak_mask_apply(tw.data_ptr(), tm.data_ptr(), te.data_ptr(), tn.data_ptr(), len(wd),
+                             max(t.numel() for t in wd), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
     _lib.check(rc, "apply")
     for w, m, e, a, b in zip(ws, ms, es, wd, ed):
         assert np.array_equal((w * m).numpy().view(np.uint32), a.cpu().numpy().view(np.uint32))   # -0.0 preserved
