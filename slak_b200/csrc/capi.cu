@@ -28,7 +28,7 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
                int N, int C, int H, int W, int KL, cudaStream_t st);
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
                int N, int C, int H, int W, int KL, int KN, int flip, cudaStream_t st);
-size_t lk3_wgrad_tc_workspace(int N, int C, int KL);
+size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL);
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
 }
@@ -146,9 +146,9 @@ SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const v
 }
 
 SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS) {
-  (void)H; (void)W; (void)KS;
+  (void)KS;
   if (N <= 0 || C <= 0 || KL <= 0) return 0;
-  return tc::lk3_wgrad_tc_workspace(N, C, KL);
+  return tc::lk3_wgrad_tc_workspace(N, C, H, W, KL);
 }
 
 SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const void* dy2, const void* dy3,
@@ -159,7 +159,7 @@ SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const v
   SLAK_REQUIRE(dy2 && dy3 && dw2 && dw3, SLAK_ERR_BAD_ARG, "null tensor pointer");
   SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
                "fused bwd_filter covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
-  const size_t need = tc::lk3_wgrad_tc_workspace(N, C, KL);
+  const size_t need = tc::lk3_wgrad_tc_workspace(N, C, H, W, KL);
   SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE, "bwd_filter workspace too small: %zu < %zu",
                workspace_bytes, need);
   return tc::lk3_wgrad_tc(x, dy1, dy2, dy3, dw1, dw2, dw3, N, C, H, W, KL, workspace, (cudaStream_t)stream);

@@ -47,7 +47,9 @@ def test_headline_shape_uses_tensor_cores_and_matches_cuda_core_path():
 
 
 TC_CASES = [(2, 3, 56, 56, 51), (5, 4, 56, 56, 51), (1, 2, 56, 56, 61), (3, 2, 48, 48, 51), (4, 3, 24, 24, 49),
-            (3, 5, 40, 56, 31), (7, 2, 16, 8, 13), (2, 2, 56, 56, 5), (33, 2, 56, 56, 51)]
+            (3, 5, 40, 56, 31), (7, 2, 16, 8, 13), (2, 2, 56, 56, 5), (33, 2, 56, 56, 51),
+            (9, 3, 28, 28, 49), (6, 2, 14, 14, 47), (11, 3, 7, 7, 13), (5, 2, 30, 22, 21), (3, 2, 13, 9, 9),
+            (17, 2, 28, 28, 5)]
 
 
 @pytest.mark.parametrize("case", TC_CASES)
