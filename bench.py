@@ -278,9 +278,11 @@ def run_ours(args):
         peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         h = HEADLINE
-        alg_bytes = 2 * h["N"] * h["C"] * h["H"] * h["W"] * 2 + h["C"] * h["kh"] * h["kw"] * 4
+        # fused three-branch forward: x read once, y1/y2/y3 written once (bf16) + the fp32 taps
+        alg_bytes = 4 * h["N"] * h["C"] * h["H"] * h["W"] * 2 + h["C"] * (2 * h["kh"] * h["kw"] + 25) * 4
         roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "kernel": "dw_fwd_fast_kernel<bf16,51x5> (stage-1 LoRA1 forward)", "peak_source": peak_src,
+                "kernel": "lk3_fwd_tc_kernel<64,16,TMA> (stage-1 fused 51x5 + 5x51 + 5x5 forward, tcgen05)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": prof["count"]}
         if prof["count"] > 0 and B == h["N"]:
             us = prof["ms_total"] * 1e3 / prof["count"]

@@ -79,11 +79,8 @@ def dwconv2d_forward(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     N, C, H, W, kh, kw = _conv_dims(x, w)
     y = torch.empty_like(x)
     lib = _lib.load()
-    timed = _profiled(N, C, H, W, kh, kw, x.dtype)
+    timed = False
     with torch.cuda.device(x.device):
-        if timed:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
         rc = lib.slak_dwconv2d_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, C, H, W, kh, kw,
                                    _lib.dtype_code(x.dtype), _lib.dtype_code(w.dtype),
                                    _lib.current_stream_ptr())
@@ -192,11 +189,18 @@ def lk_branches_forward(x, w1, w2, w3=None):
     lib = _lib.load()
     code = _lib.dtype_code(x.dtype)
     tc = w3 is not None and lib.slak_lk_branches_uses_tc(N, C, H, W, KL, KS, code)
+    timed = tc and _profiled(N, C, H, W, KL, KS, x.dtype)
     with torch.cuda.device(x.device):
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         rc = lib.slak_lk_branches_fwd(x.data_ptr(), w1.data_ptr(), w2.data_ptr(),
                                       w3.data_ptr() if w3 is not None else None,
                                       y1.data_ptr(), y2.data_ptr(), y3.data_ptr() if y3 is not None else None,
                                       N, C, H, W, KL, KS, code, _lib.current_stream_ptr())
+        if timed:
+            ev[1].record()
+            _prof["events"].append(ev)
     _lib.check(rc, "slak_lk_branches_fwd")
     _count(1 if tc else (3 if w3 is not None else 2))
     return y1, y2, y3
