@@ -122,6 +122,53 @@ SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const v
                                          size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused glue of a SLaK Block around the branches (models/SLaK.py:89-100 BN + sum, :153-166
+ * permute / LayerNorm / gamma / residual); bf16 activations, fp32 statistics and parameters.
+ * Shapes: y_i, du, dy_i [N,C,H,W] bf16 (HW = H*W); xn, h2, dxn, dh2 [N,H,W,C] bf16; x, out, dout
+ * [N,C,H,W] fp32; per-channel vectors fp32.
+ *   block_conv_fwd    : slak_lk_branches_fwd + per-channel (sum, sumsq) of y1,y2,y3 -> sums [C][6] (double)
+ *   bn3_finalize_fwd  : nn.BatchNorm2d training semantics from GLOBAL sums/count (all-reduce sums first for
+ *                       SyncBN): scale[3][C] = w*istd, shift[C] = sum_i (b_i - mean_i*scale_i), mean/istd[3][C],
+ *                       running stats updated in place (pass NULL to skip)
+ *   bn3_eval_affine   : the same affine from running statistics (eval mode)
+ *   bn3_sum_ln_fwd    : xn = LayerNorm_C(sum_i scale_i*y_i + shift), per-pixel mu/rstd saved
+ *   block_residual_fwd: out = x + dp[n]*gamma[c]*h2 (dp may be NULL = 1; out_bf16 optional copy)
+ *   block_residual_bwd: dh2 = dout*gamma*dp ; dgamma_part [parts][C] partial sums of dout*h2*dp
+ *   bn3_sum_ln_bwd    : du = LayerNorm backward of dxn ; part [parts][6][C] = dlnw, dlnb, sum du, sum du*y_i
+ *   bn3_finalize_bwd  : from GLOBAL S[4][C] -> coef[9][C] (dy_i = A_i*du + B_i*y_i + C_i), dbnw/dbnb [3][C]
+ *   bn3_bwd_apply     : dy1, dy2, dy3 in one pass
+ * ------------------------------------------------------------------------- */
+SLAK_API size_t slak_block_conv_fwd_workspace(int N, int C, int H, int W);
+SLAK_API int slak_block_conv_fwd(const void* x, const float* w1, const float* w2, const float* w3, void* y1,
+                                 void* y2, void* y3, double* sums, void* workspace, size_t workspace_bytes,
+                                 int N, int C, int H, int W, int KL, void* stream);
+/* bnw/bnb/rmean/rvar: HOST arrays of three device pointers (branch K x 5, 5 x K, 5 x 5), each [C];
+ * entries of rmean/rvar may be NULL to skip the running-statistics update */
+SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const float* const* bnw,
+                                   const float* const* bnb, float* const* rmean, float* const* rvar, float eps,
+                                   float momentum, int C, float* scale, float* shift, float* mean, float* istd,
+                                   void* stream);
+SLAK_API int slak_bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean,
+                                  const float* const* rvar, float eps, int C, float* scale, float* shift,
+                                  void* stream);
+SLAK_API int slak_bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale,
+                                 const float* shift, const float* lnw, const float* lnb, float eps, void* xn,
+                                 float* mu, float* rstd, int N, int C, int HW, void* stream);
+SLAK_API int slak_block_residual_fwd(const float* x, const void* h2, const float* gamma, const float* dp,
+                                     float* out, void* out_bf16, int N, int C, int HW, void* stream);
+SLAK_API int slak_block_residual_bwd_parts(int N, int C, int HW);
+SLAK_API int slak_block_residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp,
+                                     void* dh2, float* dgamma_part, int N, int C, int HW, void* stream);
+SLAK_API int slak_bn3_sum_ln_bwd_parts(int N, int C, int HW);
+SLAK_API int slak_bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3,
+                                 const float* scale, const float* shift, const float* lnw, const float* mu,
+                                 const float* rstd, void* du, float* part, int N, int C, int HW, void* stream);
+SLAK_API int slak_bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean,
+                                   const float* istd, int C, float* coef, float* dbnw, float* dbnb, void* stream);
+SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef,
+                                void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Sparse-mask engine (sparse_core.py:316-333, funcs.py:107-114).
  * ------------------------------------------------------------------------- */
 

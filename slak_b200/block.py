@@ -1,0 +1,234 @@
+"""Fused SLaK Block (models/SLaK.py:153-166 with the Decom large-kernel branch of :89-100) as ONE
+autograd node over the C ABI:
+
+  forward   cast -> [tcgen05] three depthwise branches + BN statistics -> BN finalize (+ SyncBN
+            all-reduce of the per-channel sums) -> BN apply + sum + NCHW->NHWC + LayerNorm (1 pass) ->
+            Linear / GELU / Linear (cuBLAS through torch.mm, bf16) -> gamma * . + residual (1 pass)
+  backward  the mirror image: residual/gamma -> MLP backward -> LayerNorm backward + BatchNorm
+            reductions (1 pass) -> BN backward apply for the 3 branches (1 pass) -> [tcgen05] fused
+            dgrad + wgrad
+
+Numerics: bf16 activations between the stages, fp32 statistics / parameters / residual stream --
+the dataflow of the reference under autocast with the depthwise branch made autocast-eligible.
+Used by slak_b200.slak.Block when the layout allows (CUDA, fp32 residual stream, autocast bf16,
+Decom with the small branch, BN on, tensor-core plane sizes); everything else takes the
+module-by-module path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ptr3(a, b, c):
+    return (ctypes.c_void_p * 3)(_p(a), _p(b), _p(c))
+
+
+def _ck(rc, what):
+    _lib.check(rc, what)
+
+
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size()
+    return None, 1
+
+
+class FusedBlockFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, w2, w3, bw1, bw2, bw3, bb1, bb2, bb3, lnw, lnb, W1, b1, W2, b2, gamma, dp, cfg):
+        lib = _lib.load()
+        st = _lib.current_stream_ptr()
+        N, C, H, W = x.shape
+        HW = H * W
+        KL = w1.size(2)
+        dev = x.device
+        bf16 = torch.bfloat16
+        xb = x.to(bf16)
+        y1, y2, y3 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
+        scale = torch.empty((3, C), dtype=torch.float32, device=dev)
+        shift = torch.empty((C,), dtype=torch.float32, device=dev)
+        training = cfg["training"]
+        sync = cfg["sync_bn"]
+        if training:
+            sums = torch.empty((C, 6), dtype=torch.float64, device=dev)
+            need = lib.slak_block_conv_fwd_workspace(N, C, H, W)
+            ws = ops._workspace(need, dev)
+            _ck(lib.slak_block_conv_fwd(_p(xb), _p(w1), _p(w2), _p(w3), _p(y1), _p(y2), _p(y3), _p(sums), _p(ws),
+                                        ws.numel(), N, C, H, W, KL, st), "slak_block_conv_fwd")
+            count = float(N * HW)
+            dist, world = _dist_world() if sync else (None, 1)
+            if world > 1:                     # SyncBatchNorm: statistics over the global batch
+                dist.all_reduce(sums)
+                count *= world
+            mean = torch.empty((3, C), dtype=torch.float32, device=dev)
+            istd = torch.empty((3, C), dtype=torch.float32, device=dev)
+            rm, rv = cfg["running_mean"], cfg["running_var"]
+            _ck(lib.slak_bn3_finalize_fwd(_p(sums), count, _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3), _ptr3(*rm),
+                                          _ptr3(*rv), cfg["bn_eps"], cfg["bn_momentum"], C, _p(scale), _p(shift),
+                                          _p(mean), _p(istd), st), "slak_bn3_finalize_fwd")
+            for nbt in cfg["num_batches_tracked"]:
+                if nbt is not None:
+                    nbt.add_(1)
+            ops._count(3)
+        else:
+            ys = ops.lk_branches_forward(xb, w1, w2, w3)
+            y1, y2, y3 = ys
+            rm, rv = cfg["running_mean"], cfg["running_var"]
+            _ck(lib.slak_bn3_eval_affine(_ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3), _ptr3(*rm), _ptr3(*rv),
+                                         cfg["bn_eps"], C, _p(scale), _p(shift), st), "slak_bn3_eval_affine")
+            mean = istd = None
+            count = float(N * HW)
+            ops._count(1)
+        xn = torch.empty((N, H, W, C), dtype=bf16, device=dev)
+        mu = torch.empty((N * HW,), dtype=torch.float32, device=dev)
+        rstd = torch.empty((N * HW,), dtype=torch.float32, device=dev)
+        _ck(lib.slak_bn3_sum_ln_fwd(_p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(lnb), cfg["ln_eps"],
+                                    _p(xn), _p(mu), _p(rstd), N, C, HW, st), "slak_bn3_sum_ln_fwd")
+        # pointwise MLP (cuBLAS): bf16 operands, fp32 accumulate
+        W1b, W2b = W1.to(bf16), W2.to(bf16)
+        xf = xn.view(N * HW, C)
+        h = torch.addmm(b1.to(bf16), xf, W1b.t())
+        a = F.gelu(h)
+        h2 = torch.addmm(b2.to(bf16), a, W2b.t())
+        del a
+        out = torch.empty_like(x)
+        _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), None, N, C, HW, st),
+            "slak_block_residual_fwd")
+        ops._count(2)
+        ctx.cfg = cfg
+        ctx.count = count
+        ctx.dims = (N, C, H, W, KL)
+        ctx.save_for_backward(xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd,
+                              xn, h, h2, W1b, W2b, gamma, dp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd, xn, h, h2, W1b, W2b,
+         gamma, dp) = ctx.saved_tensors
+        cfg = ctx.cfg
+        if not cfg["training"]:
+            raise RuntimeError("FusedBlockFunction.backward is only defined for training-mode BatchNorm")
+        lib = _lib.load()
+        st = _lib.current_stream_ptr()
+        N, C, H, W, KL = ctx.dims
+        HW = H * W
+        dev = dout.device
+        bf16 = torch.bfloat16
+        dout = dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        # ---- residual / gamma ---------------------------------------------------------------------
+        parts = lib.slak_block_residual_bwd_parts(N, C, HW)
+        dh2 = torch.empty((N * HW, C), dtype=bf16, device=dev)
+        dgp = torch.empty((parts, C), dtype=torch.float32, device=dev)
+        _ck(lib.slak_block_residual_bwd(_p(dout), _p(h2), _p(gamma), _p(dp), _p(dh2), _p(dgp), N, C, HW, st),
+            "slak_block_residual_bwd")
+        dgamma = dgp.sum(0)
+        # ---- MLP backward (cuBLAS) -----------------------------------------------------------------
+        a = F.gelu(h)
+        dW2 = torch.mm(dh2.t(), a).float()
+        db2 = dh2.sum(0, dtype=torch.float32)
+        da = torch.mm(dh2, W2b)
+        del a
+        dh = torch.ops.aten.gelu_backward(da, h)
+        del da
+        xf = xn.view(N * HW, C)
+        dW1 = torch.mm(dh.t(), xf).float()
+        db1 = dh.sum(0, dtype=torch.float32)
+        dxn = torch.mm(dh, W1b)
+        del dh
+        # ---- LayerNorm backward + BatchNorm reductions ------------------------------------------------
+        parts = lib.slak_bn3_sum_ln_bwd_parts(N, C, HW)
+        du = torch.empty_like(xb)
+        part = torch.empty((parts, 6, C), dtype=torch.float32, device=dev)
+        _ck(lib.slak_bn3_sum_ln_bwd(_p(dxn), _p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(mu), _p(rstd),
+                                    _p(du), _p(part), N, C, HW, st), "slak_bn3_sum_ln_bwd")
+        red = part.sum(0)                        # [6][C]
+        dlnw, dlnb = red[0], red[1]
+        S = red[2:6].contiguous()
+        if cfg["sync_bn"]:
+            dist, world = _dist_world()
+            if world > 1:
+                dist.all_reduce(S)
+        coef = torch.empty((9, C), dtype=torch.float32, device=dev)
+        dbnw = torch.empty((3, C), dtype=torch.float32, device=dev)
+        dbnb = torch.empty((3, C), dtype=torch.float32, device=dev)
+        _ck(lib.slak_bn3_finalize_bwd(_p(S), ctx.count, _ptr3(bw1, bw2, bw3), _p(mean), _p(istd), C, _p(coef),
+                                      _p(dbnw), _p(dbnb), st), "slak_bn3_finalize_bwd")
+        dy1, dy2, dy3 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
+        _ck(lib.slak_bn3_bwd_apply(_p(du), _p(y1), _p(y2), _p(y3), _p(coef), _p(dy1), _p(dy2), _p(dy3), N, C, HW, st),
+            "slak_bn3_bwd_apply")
+        del du
+        ops._count(4)
+        # ---- depthwise branches: fused tensor-core dgrad / wgrad ------------------------------------------
+        dxc = ops.lk_branches_backward_data(dy1, dy2, dy3, w1, w2, w3)
+        dw1, dw2, dw3 = ops.lk_branches_backward_filter(xb, dy1, dy2, dy3, KL, 5)
+        dx = dout + dxc                           # shortcut + branch gradient, fp32
+        return (dx, dw1, dw2, dw3, dbnw[0], dbnw[1], dbnw[2], dbnb[0], dbnb[1], dbnb[2], dlnw, dlnb,
+                dW1, db1, dW2, db2, dgamma, None, None)
+
+
+def fused_block_supported(block, x) -> bool:
+    """Can `block` (slak_b200.slak.Block) run through FusedBlockFunction on input x?"""
+    lk = block.large_kernel
+    if not (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous()):
+        return False
+    if not (torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16):
+        return False
+    if not (getattr(lk, "Decom", False) and hasattr(lk, "small_conv") and hasattr(lk, "LoRA1") and block.gamma is not None):
+        return False
+    if lk.small_kernel != 5 or not all(hasattr(b, "bn") for b in (lk.LoRA1, lk.LoRA2, lk.small_conv)):
+        return False
+    if not block.training and torch.is_grad_enabled():
+        return False                           # eval-mode BN backward is not implemented in the fused node
+    N, C, H, W = x.shape
+    if C > 1024 or block.norm.data_format != "channels_last":
+        return False
+    if not all(bn.affine and bn.weight.dtype == torch.float32 for bn in (lk.LoRA1.bn, lk.LoRA2.bn, lk.small_conv.bn)):
+        return False
+    return ops.lk_branches_uses_tc(_Shape(N, C, H, W), lk.kernel_size, 5)
+
+
+class _Shape:
+    """Minimal stand-in carrying .shape/.dtype for ops.lk_branches_uses_tc."""
+
+    def __init__(self, N, C, H, W):
+        self.shape = (N, C, H, W)
+        self.dtype = torch.bfloat16
+
+
+def fused_block_forward(block, x):
+    lk = block.large_kernel
+    bns = (lk.LoRA1.bn, lk.LoRA2.bn, lk.small_conv.bn)
+    sync = isinstance(bns[0], torch.nn.SyncBatchNorm)
+    track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)
+    training = block.training or not track
+    cfg = {
+        "training": training, "sync_bn": sync,
+        "bn_eps": float(bns[0].eps), "bn_momentum": float(bns[0].momentum if bns[0].momentum is not None else 0.1),
+        "ln_eps": float(block.norm.eps),
+        "running_mean": tuple(bn.running_mean if (track and block.training) or not training else None for bn in bns),
+        "running_var": tuple(bn.running_var if (track and block.training) or not training else None for bn in bns),
+        "num_batches_tracked": tuple(bn.num_batches_tracked if (track and block.training) else None for bn in bns),
+    }
+    dp = None
+    p = getattr(block.drop_path, "drop_prob", 0.0)
+    if block.training and p > 0.0:
+        keep = 1.0 - p
+        dp = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device).bernoulli_(keep).div_(keep)
+    return FusedBlockFunction.apply(
+        x, lk.LoRA1.conv.weight, lk.LoRA2.conv.weight, lk.small_conv.conv.weight,
+        bns[0].weight, bns[1].weight, bns[2].weight, bns[0].bias, bns[1].bias, bns[2].bias,
+        block.norm.weight, block.norm.bias, block.pwconv1.weight, block.pwconv1.bias, block.pwconv2.weight,
+        block.pwconv2.bias, block.gamma, dp, cfg)

@@ -1,0 +1,615 @@
+// Memory-bound glue of a SLaK Block around the depthwise branches, fused into a few passes
+// (models/SLaK.py:89-100 BN+sum, :153-166 permute / LayerNorm / gamma / residual):
+//
+//   bn3_finalize_fwd   per-channel batch statistics of the three branch outputs -> BN scale/shift,
+//                      running-stat update                                  (nn.BatchNorm2d semantics)
+//   bn3_sum_ln_fwd     xn[n,h,w,:] = LayerNorm_C( sum_i scale_i*y_i + shift )   NCHW bf16 x3 -> NHWC bf16
+//   residual_fwd       out = x + dp[n]*gamma[c]*h2[n,h,w,c]                       NHWC bf16 -> NCHW fp32
+//   residual_bwd       d_h2 = dOut*gamma*dp (NHWC bf16), per-CTA partial of dgamma
+//   bn3_sum_ln_bwd     LayerNorm backward per pixel -> du (NCHW bf16) + per-CTA partials of dln_w,
+//                      dln_b and of the BatchNorm reductions sum(du), sum(du*y_i)
+//   bn3_finalize_bwd   BatchNorm backward coefficients: dy_i = A_i*du + B_i*y_i + C_i, dgamma_i, dbeta_i
+//   bn3_bwd_apply      dy_i (NCHW bf16) for the three branches in one pass
+//
+// All kernels work on a (C x PIX) tile of one image staged in shared memory as fp32, so that the
+// NCHW side is accessed along pixels and the NHWC side along channels (both coalesced); LayerNorm
+// runs one warp per pixel with lanes over channels.  Reductions are per-CTA partials combined in a
+// fixed order (deterministic).
+#include "common.cuh"
+
+namespace slak {
+namespace blk {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+// load VP consecutive bf16 -> float
+template <int VP>
+__device__ __forceinline__ void ld_bf16(const __nv_bfloat16* p, float* f) {
+  if constexpr (VP == 8) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+  } else if constexpr (VP == 4) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { const float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+  } else {
+    f[0] = __bfloat162float(*p);
+  }
+}
+template <int VP>
+__device__ __forceinline__ void st_bf16(__nv_bfloat16* p, const float* f) {
+  if constexpr (VP == 8) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  } else if constexpr (VP == 4) {
+    uint2 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<uint2*>(p) = r;
+  } else {
+    *p = __float2bfloat16_rn(f[0]);
+  }
+}
+
+struct Geo {
+  int N, C, HW, PIX, tiles_per_img, total_tiles, pitch;
+};
+
+// ------------------------------------------------------------------------------------------
+// forward: BN(3) + sum + LayerNorm, NCHW -> NHWC
+// ------------------------------------------------------------------------------------------
+template <int VP>
+__global__ void __launch_bounds__(kThreads)
+bn3_sum_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y1, const __nv_bfloat16* __restrict__ y2,
+                      const __nv_bfloat16* __restrict__ y3, const float* __restrict__ scale /*[3][C]*/,
+                      const float* __restrict__ shift /*[C]*/, const float* __restrict__ lnw,
+                      const float* __restrict__ lnb, float eps, __nv_bfloat16* __restrict__ xn,
+                      float* __restrict__ mu, float* __restrict__ rstd, Geo g) {
+  extern __shared__ float tile[];   // [C][pitch]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
+  const int vec_per_row = PIX / VP;
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
+    const int npix = min(PIX, HW - p0);
+    __syncthreads();
+    for (int idx = tid; idx < C * vec_per_row; idx += kThreads) {
+      const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
+      const int j = jv * VP;
+      if (j < npix) {
+        const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+        float a[VP], b[VP], d[VP];
+        ld_bf16<VP>(y1 + off, a); ld_bf16<VP>(y2 + off, b); ld_bf16<VP>(y3 + off, d);
+        const float s1 = scale[c], s2 = scale[C + c], s3 = scale[2 * C + c], sh = shift[c];
+#pragma unroll
+        for (int k = 0; k < VP; ++k) tile[c * pitch + j + k] = fmaf(s1, a[k], fmaf(s2, b[k], fmaf(s3, d[k], sh)));
+      }
+    }
+    __syncthreads();
+    for (int j = warp; j < npix; j += kWarps) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += tile[c * pitch + j];
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+      for (int c = lane; c < C; c += 32) { const float d = tile[c * pitch + j] - mean; q = fmaf(d, d, q); }
+      const float r = rsqrtf(warp_sum(q) / C + eps);
+      const size_t pix = (size_t)n * HW + p0 + j;
+      if (lane == 0) { mu[pix] = mean; rstd[pix] = r; }
+      __nv_bfloat16* o = xn + pix * C;
+      if ((C & 1) == 0) {
+        for (int c = 2 * lane; c < C; c += 64) {
+          const float v0 = (tile[c * pitch + j] - mean) * r * lnw[c] + lnb[c];
+          const float v1 = (tile[(c + 1) * pitch + j] - mean) * r * lnw[c + 1] + lnb[c + 1];
+          *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(v0, v1);
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) o[c] = __float2bfloat16_rn((tile[c * pitch + j] - mean) * r * lnw[c] + lnb[c]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: out = x + dp*gamma*h2^T
+// ------------------------------------------------------------------------------------------
+template <int VP>
+__global__ void __launch_bounds__(kThreads)
+residual_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ h2,
+                    const float* __restrict__ gamma, const float* __restrict__ dp /*[N] or null*/,
+                    float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16 /*or null*/, Geo g) {
+  extern __shared__ float tile[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
+  const int vec_per_row = PIX / VP;
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
+    const int npix = min(PIX, HW - p0);
+    const float dps = dp ? dp[n] : 1.f;
+    __syncthreads();
+    for (int j = warp; j < npix; j += kWarps) {
+      const __nv_bfloat16* hp = h2 + ((size_t)n * HW + p0 + j) * C;
+      if ((C & 1) == 0) {
+        for (int c = 2 * lane; c < C; c += 64) {
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + c));
+          tile[c * pitch + j] = v.x * gamma[c] * dps;
+          tile[(c + 1) * pitch + j] = v.y * gamma[c + 1] * dps;
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) tile[c * pitch + j] = bf(hp[c]) * gamma[c] * dps;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < C * vec_per_row; idx += kThreads) {
+      const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
+      const int j = jv * VP;
+      if (j < npix) {
+        const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+        float o[VP];
+        if constexpr (VP >= 4) {
+#pragma unroll
+          for (int k = 0; k < VP; k += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + off + k);
+            o[k] = xv.x + tile[c * pitch + j + k]; o[k + 1] = xv.y + tile[c * pitch + j + k + 1];
+            o[k + 2] = xv.z + tile[c * pitch + j + k + 2]; o[k + 3] = xv.w + tile[c * pitch + j + k + 3];
+          }
+        } else {
+          o[0] = x[off] + tile[c * pitch + j];
+        }
+        if constexpr (VP >= 4) {
+#pragma unroll
+          for (int k = 0; k < VP; k += 4) *reinterpret_cast<float4*>(out + off + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+        } else {
+          out[off] = o[0];
+        }
+        if (out_bf16) st_bf16<VP>(out_bf16 + off, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: d_h2 = dOut*gamma*dp (NHWC bf16); partial dgamma[cta][C] = sum dOut*h2*dp
+// ------------------------------------------------------------------------------------------
+template <int VP>
+__global__ void __launch_bounds__(kThreads)
+residual_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h2,
+                    const float* __restrict__ gamma, const float* __restrict__ dp,
+                    __nv_bfloat16* __restrict__ dh2, float* __restrict__ dgamma_part /*[grid][C]*/, Geo g) {
+  extern __shared__ float tile[];
+  float* acc = tile + (size_t)g.C * g.pitch;   // [kWarps][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
+  const int vec_per_row = PIX / VP;
+  for (int i = tid; i < kWarps * C; i += kThreads) acc[i] = 0.f;
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
+    const int npix = min(PIX, HW - p0);
+    const float dps = dp ? dp[n] : 1.f;
+    __syncthreads();
+    for (int idx = tid; idx < C * vec_per_row; idx += kThreads) {
+      const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
+      const int j = jv * VP;
+      if (j < npix) {
+        const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+        if constexpr (VP >= 4) {
+#pragma unroll
+          for (int k = 0; k < VP; k += 4) {
+            const float4 dv = *reinterpret_cast<const float4*>(dout + off + k);
+            tile[c * pitch + j + k] = dv.x; tile[c * pitch + j + k + 1] = dv.y;
+            tile[c * pitch + j + k + 2] = dv.z; tile[c * pitch + j + k + 3] = dv.w;
+          }
+        } else {
+          tile[c * pitch + j] = dout[off];
+        }
+      }
+    }
+    __syncthreads();
+    for (int j = warp; j < npix; j += kWarps) {
+      const size_t pix = (size_t)n * HW + p0 + j;
+      const __nv_bfloat16* hp = h2 + pix * C;
+      __nv_bfloat16* dp_out = dh2 + pix * C;
+      if ((C & 1) == 0) {
+        for (int c = 2 * lane; c < C; c += 64) {
+          const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + c));
+          const float g0 = tile[c * pitch + j] * dps, g1 = tile[(c + 1) * pitch + j] * dps;
+          *reinterpret_cast<__nv_bfloat162*>(dp_out + c) = __floats2bfloat162_rn(g0 * gamma[c], g1 * gamma[c + 1]);
+          acc[warp * C + c] += g0 * h.x;
+          acc[warp * C + c + 1] += g1 * h.y;
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) {
+          const float g0 = tile[c * pitch + j] * dps;
+          dp_out[c] = __float2bfloat16_rn(g0 * gamma[c]);
+          acc[warp * C + c] += g0 * bf(hp[c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += acc[w * C + c];
+    dgamma_part[(size_t)blockIdx.x * C + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: LayerNorm backward + BatchNorm reductions.  part layout per CTA: [6][C] =
+//   dlnw, dlnb, S0 = sum du, S1..S3 = sum du*y_i
+// ------------------------------------------------------------------------------------------
+template <int VP>
+__global__ void __launch_bounds__(kThreads)
+bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16* __restrict__ y1,
+                      const __nv_bfloat16* __restrict__ y2, const __nv_bfloat16* __restrict__ y3,
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ lnw, const float* __restrict__ mu, const float* __restrict__ rstd,
+                      __nv_bfloat16* __restrict__ du, float* __restrict__ part /*[grid][6][C]*/, Geo g) {
+  extern __shared__ float tile[];
+  const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
+  float* accw = tile + (size_t)C * pitch;      // [kWarps][2][C]  dlnw, dlnb per warp
+  float* accs = accw + kWarps * 2 * C;         // [4][C]          S0..S3 (each channel owned by one warp)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int vec_per_row = PIX / VP;
+  for (int i = tid; i < kWarps * 2 * C + 4 * C; i += kThreads) accw[i] = 0.f;
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
+    const int npix = min(PIX, HW - p0);
+    __syncthreads();
+    // phase 1: recompute u = sum_i scale_i*y_i + shift
+    for (int idx = tid; idx < C * vec_per_row; idx += kThreads) {
+      const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
+      const int j = jv * VP;
+      if (j < npix) {
+        const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+        float a[VP], b[VP], d[VP];
+        ld_bf16<VP>(y1 + off, a); ld_bf16<VP>(y2 + off, b); ld_bf16<VP>(y3 + off, d);
+        const float s1 = scale[c], s2 = scale[C + c], s3 = scale[2 * C + c], sh = shift[c];
+#pragma unroll
+        for (int k = 0; k < VP; ++k) tile[c * pitch + j + k] = fmaf(s1, a[k], fmaf(s2, b[k], fmaf(s3, d[k], sh)));
+      }
+    }
+    __syncthreads();
+    // phase 2: per pixel LayerNorm backward, du overwrites u in the tile
+    for (int j = warp; j < npix; j += kWarps) {
+      const size_t pix = (size_t)n * HW + p0 + j;
+      const float m = mu[pix], r = rstd[pix];
+      const __nv_bfloat16* gp = dxn + pix * C;
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float gx = bf(gp[c]);
+        const float xh = (tile[c * pitch + j] - m) * r;
+        const float gg = gx * lnw[c];
+        s1 += gg; s2 = fmaf(gg, xh, s2);
+        accw[(warp * 2 + 0) * C + c] = fmaf(gx, xh, accw[(warp * 2 + 0) * C + c]);
+        accw[(warp * 2 + 1) * C + c] += gx;
+      }
+      const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+      for (int c = lane; c < C; c += 32) {
+        const float xh = (tile[c * pitch + j] - m) * r;
+        const float gg = bf(gp[c]) * lnw[c];
+        tile[c * pitch + j] = r * (gg - m1 - xh * m2);
+      }
+    }
+    __syncthreads();
+    // phase 3: write du (NCHW bf16) and accumulate the BatchNorm reductions; one warp per channel
+    for (int c = warp; c < C; c += kWarps) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int jv = lane; jv < vec_per_row; jv += 32) {
+        const int j = jv * VP;
+        if (j < npix) {
+          const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+          float d[VP], q1[VP], q2[VP], q3[VP];
+#pragma unroll
+          for (int k = 0; k < VP; ++k) d[k] = tile[c * pitch + j + k];
+          st_bf16<VP>(du + off, d);
+          ld_bf16<VP>(y1 + off, q1); ld_bf16<VP>(y2 + off, q2); ld_bf16<VP>(y3 + off, q3);
+#pragma unroll
+          for (int k = 0; k < VP; ++k) {
+            const float dr = __bfloat162float(__float2bfloat16_rn(d[k]));   // the value BN backward will see
+            a0 += dr; a1 = fmaf(dr, q1[k], a1); a2 = fmaf(dr, q2[k], a2); a3 = fmaf(dr, q3[k], a3);
+          }
+        }
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+      if (lane == 0) { accs[c] += a0; accs[C + c] += a1; accs[2 * C + c] += a2; accs[3 * C + c] += a3; }
+    }
+  }
+  __syncthreads();
+  float* o = part + (size_t)blockIdx.x * 6 * C;
+  for (int c = tid; c < C; c += kThreads) {
+    float w0 = 0.f, w1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { w0 += accw[(w * 2 + 0) * C + c]; w1 += accw[(w * 2 + 1) * C + c]; }
+    o[c] = w0; o[C + c] = w1;
+    o[2 * C + c] = accs[c]; o[3 * C + c] = accs[C + c]; o[4 * C + c] = accs[2 * C + c]; o[5 * C + c] = accs[3 * C + c];
+  }
+}
+
+// dy_i = A_i*du + B_i*y_i + C_i   (coef: [9][C] = A1..A3, B1..B3, C1..C3)
+template <int VP>
+__global__ void __launch_bounds__(kThreads)
+bn3_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ y1,
+                     const __nv_bfloat16* __restrict__ y2, const __nv_bfloat16* __restrict__ y3,
+                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy1,
+                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dy3, int C, int HW, size_t planes) {
+  const int vec_per_plane = HW / VP;
+  const size_t total = planes * vec_per_plane;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    const size_t plane = i / vec_per_plane;
+    const int c = (int)(plane % C);
+    const size_t off = i * VP;
+    float d[VP], a[VP], b[VP], e[VP], o[VP];
+    ld_bf16<VP>(du + off, d); ld_bf16<VP>(y1 + off, a); ld_bf16<VP>(y2 + off, b); ld_bf16<VP>(y3 + off, e);
+    const float A1 = coef[c], A2 = coef[C + c], A3 = coef[2 * C + c];
+    const float B1 = coef[3 * C + c], B2 = coef[4 * C + c], B3 = coef[5 * C + c];
+    const float C1 = coef[6 * C + c], C2 = coef[7 * C + c], C3 = coef[8 * C + c];
+#pragma unroll
+    for (int k = 0; k < VP; ++k) o[k] = fmaf(A1, d[k], fmaf(B1, a[k], C1));
+    st_bf16<VP>(dy1 + off, o);
+#pragma unroll
+    for (int k = 0; k < VP; ++k) o[k] = fmaf(A2, d[k], fmaf(B2, b[k], C2));
+    st_bf16<VP>(dy2 + off, o);
+#pragma unroll
+    for (int k = 0; k < VP; ++k) o[k] = fmaf(A3, d[k], fmaf(B3, e[k], C3));
+    st_bf16<VP>(dy3 + off, o);
+  }
+}
+
+// per-channel batch statistics from the conv kernel's per-CTA partials -> BN scale/shift (training)
+//   part: [C][splits][6] = (sum, sumsq) x 3 branches ; stats_out: [C][6] (sum, sumsq totals, for SyncBN)
+__global__ void bn3_reduce_partials_kernel(const float* __restrict__ part, int splits, int C, double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over C*6
+  if (i >= C * 6) return;
+  const int c = i / 6, k = i - c * 6;
+  double s = 0.0;
+  for (int sp = 0; sp < splits; ++sp) s += (double)part[((size_t)c * splits + sp) * 6 + k];
+  sums[i] = s;
+}
+// sums: [C][6] doubles (global over all ranks), count = N*H*W (global)
+// bnw/bnb: [3][C]; running_mean/var: [3][C] (updated in place when momentum >= 0)
+// out: scale[3][C], shift[C], mean[3][C], istd[3][C]
+struct P3 { const float* p[3]; };
+struct M3 { float* p[3]; };
+__global__ void bn3_finalize_fwd_kernel(const double* __restrict__ sums, double count, P3 bnw, P3 bnb, M3 rmean, M3 rvar,
+                                        float eps, float momentum, int C, float* __restrict__ scale,
+                                        float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ istd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sh = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double m = sums[c * 6 + 2 * i] / count;
+    double var = sums[c * 6 + 2 * i + 1] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = bnw.p[i][c] * is;
+    scale[i * C + c] = sc;
+    mean[i * C + c] = (float)m;
+    istd[i * C + c] = is;
+    sh += bnb.p[i][c] - (float)m * sc;
+    if (rmean.p[i]) {
+      const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+      rmean.p[i][c] = (1.f - momentum) * rmean.p[i][c] + momentum * (float)m;
+      rvar.p[i][c] = (1.f - momentum) * rvar.p[i][c] + momentum * (float)unb;
+    }
+  }
+  shift[c] = sh;
+}
+// eval mode: scale/shift from the running statistics
+__global__ void bn3_eval_affine_kernel(P3 bnw, P3 bnb, P3 rmean, P3 rvar, float eps, int C,
+                                       float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sh = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float sc = bnw.p[i][c] * rsqrtf(rvar.p[i][c] + eps);
+    scale[i * C + c] = sc;
+    sh += bnb.p[i][c] - rmean.p[i][c] * sc;
+  }
+  shift[c] = sh;
+}
+// S: [4][C] = sum du, sum du*y_i (global) ; out coef [9][C], dbnw[3][C], dbnb[3][C]
+__global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, double count, P3 bnw,
+                                        const float* __restrict__ mean, const float* __restrict__ istd, int C,
+                                        float* __restrict__ coef, float* __restrict__ dbnw, float* __restrict__ dbnb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double S0 = S[c];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double m = mean[i * C + c], is = istd[i * C + c], w = bnw.p[i][c];
+    const double Si = S[(i + 1) * C + c];
+    const double D = is * (Si - m * S0);            // sum du * yhat_i
+    const double a = w * is;
+    coef[i * C + c] = (float)a;
+    coef[(3 + i) * C + c] = (float)(-a * is * D / count);
+    coef[(6 + i) * C + c] = (float)(-a * S0 / count + a * is * m * D / count);
+    dbnw[i * C + c] = (float)D;
+    dbnb[i * C + c] = (float)S0;
+  }
+}
+
+// ---- host launchers -------------------------------------------------------------------------
+static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_bytes) {
+  Geo g{};
+  g.N = N; g.C = C; g.HW = HW;
+  // tile of PIX pixels x C channels in fp32; PIX a multiple of 8, about 48 KB
+  int pix = (48 * 1024 / 4) / C;
+  pix = pix >= 128 ? 128 : (pix >= 64 ? 64 : (pix >= 32 ? 32 : (pix >= 16 ? 16 : 8)));
+  while (pix > 8 && pix / 2 >= HW) pix /= 2;
+  g.PIX = pix;
+  g.pitch = pix + 1;
+  g.tiles_per_img = (HW + pix - 1) / pix;
+  g.total_tiles = g.tiles_per_img * N;
+  *smem_bytes = ((size_t)C * g.pitch + (size_t)extra_floats_per_c * C) * sizeof(float);
+  return g;
+}
+static int pick_vp(int HW, const void* a, const void* b, const void* c, const void* d) {
+  const uintptr_t m = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                      reinterpret_cast<uintptr_t>(d);
+  if (HW % 8 == 0 && (m & 15) == 0) return 8;
+  if (HW % 4 == 0 && (m & 7) == 0) return 4;
+  return 1;
+}
+static int grid_for(const Geo& g, size_t smem) {
+  int per_sm = smem > 0 ? (int)(200 * 1024 / smem) : 4;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int grid = sm_count() * per_sm;
+  if (grid > g.total_tiles) grid = g.total_tiles;
+  return grid < 1 ? 1 : grid;
+}
+
+#define SLAK_VP_DISPATCH(vp, CALL)               \
+  do {                                           \
+    if ((vp) == 8) { CALL(8); }                  \
+    else if ((vp) == 4) { CALL(4); }             \
+    else { CALL(1); }                            \
+  } while (0)
+
+int bn3_stats_finalize(const float* part, int splits, double* sums_ws, int C, cudaStream_t st) {
+  bn3_reduce_partials_kernel<<<(C * 6 + 127) / 128, 128, 0, st>>>(part, splits, C, sums_ws);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+int bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
+                     float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale, float* shift,
+                     float* mean, float* istd, cudaStream_t st) {
+  P3 w{{bnw[0], bnw[1], bnw[2]}}, b{{bnb[0], bnb[1], bnb[2]}};
+  M3 rm{{rmean[0], rmean[1], rmean[2]}}, rv{{rvar[0], rvar[1], rvar[2]}};
+  bn3_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, count, w, b, rm, rv, eps, momentum, C, scale, shift, mean, istd);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+int bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean, const float* const* rvar,
+                    float eps, int C, float* scale, float* shift, cudaStream_t st) {
+  P3 w{{bnw[0], bnw[1], bnw[2]}}, b{{bnb[0], bnb[1], bnb[2]}}, rm{{rmean[0], rmean[1], rmean[2]}}, rv{{rvar[0], rvar[1], rvar[2]}};
+  bn3_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(w, b, rm, rv, eps, C, scale, shift);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+int bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean, const float* istd, int C,
+                     float* coef, float* dbnw, float* dbnb, cudaStream_t st) {
+  P3 w{{bnw[0], bnw[1], bnw[2]}};
+  bn3_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(S, count, w, mean, istd, C, coef, dbnw, dbnb);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, const float* shift,
+                   const float* lnw, const float* lnb, float eps, void* xn, float* mu, float* rstd, int N, int C, int HW,
+                   cudaStream_t st) {
+  size_t smem;
+  Geo g = make_geo(N, C, HW, 0, &smem);
+  SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
+  const int vp = pick_vp(HW, y1, y2, y3, y1);
+  const int grid = grid_for(g, smem);
+#define CALL(V)                                                                                                   \
+  SLAK_CUDA_TRY(cudaFuncSetAttribute(bn3_sum_ln_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  bn3_sum_ln_fwd_kernel<V><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)y1, (const __nv_bfloat16*)y2,        \
+      (const __nv_bfloat16*)y3, scale, shift, lnw, lnb, eps, (__nv_bfloat16*)xn, mu, rstd, g)
+  SLAK_VP_DISPATCH(vp, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+int residual_fwd(const float* x, const void* h2, const float* gamma, const float* dp, float* out, void* out_bf16,
+                 int N, int C, int HW, cudaStream_t st) {
+  size_t smem;
+  Geo g = make_geo(N, C, HW, 0, &smem);
+  SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
+  int vp = pick_vp(HW, x, out, out_bf16, x);
+  if (vp == 8 && HW % 8 != 0) vp = 1;
+  const int grid = grid_for(g, smem);
+#define CALL(V)                                                                                                   \
+  SLAK_CUDA_TRY(cudaFuncSetAttribute(residual_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  residual_fwd_kernel<V><<<grid, kThreads, smem, st>>>(x, (const __nv_bfloat16*)h2, gamma, dp, out, (__nv_bfloat16*)out_bf16, g)
+  SLAK_VP_DISPATCH(vp, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+int residual_bwd_parts(int N, int C, int HW) {
+  size_t smem;
+  Geo g = make_geo(N, C, HW, kWarps, &smem);
+  return grid_for(g, smem);
+}
+int residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2, float* dgamma_part,
+                 int N, int C, int HW, cudaStream_t st) {
+  size_t smem;
+  Geo g = make_geo(N, C, HW, kWarps, &smem);
+  SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
+  const int vp = pick_vp(HW, dout, dout, dout, dout);
+  const int grid = grid_for(g, smem);
+#define CALL(V)                                                                                                   \
+  SLAK_CUDA_TRY(cudaFuncSetAttribute(residual_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  residual_bwd_kernel<V><<<grid, kThreads, smem, st>>>(dout, (const __nv_bfloat16*)h2, gamma, dp, (__nv_bfloat16*)dh2, dgamma_part, g)
+  SLAK_VP_DISPATCH(vp, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+int bn3_sum_ln_bwd_parts(int N, int C, int HW) {
+  size_t smem;
+  Geo g = make_geo(N, C, HW, kWarps * 2 + 4, &smem);
+  return grid_for(g, smem);
+}
+int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
+                   const float* shift, const float* lnw, const float* mu, const float* rstd, void* du, float* part,
+                   int N, int C, int HW, cudaStream_t st) {
+  size_t smem;
+  Geo g = make_geo(N, C, HW, kWarps * 2 + 4, &smem);
+  SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
+  const int vp = pick_vp(HW, y1, y2, y3, du);
+  const int grid = grid_for(g, smem);
+#define CALL(V)                                                                                                   \
+  SLAK_CUDA_TRY(cudaFuncSetAttribute(bn3_sum_ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  bn3_sum_ln_bwd_kernel<V><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)dxn, (const __nv_bfloat16*)y1,       \
+      (const __nv_bfloat16*)y2, (const __nv_bfloat16*)y3, scale, shift, lnw, mu, rstd, (__nv_bfloat16*)du, part, g)
+  SLAK_VP_DISPATCH(vp, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+int bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef, void* dy1,
+                  void* dy2, void* dy3, int N, int C, int HW, cudaStream_t st) {
+  int vp = pick_vp(HW, du, y1, y2, y3);
+  const int vp2 = pick_vp(HW, dy1, dy2, dy3, dy1);
+  if (vp2 < vp) vp = vp2;
+  const size_t planes = (size_t)N * C;
+  const size_t total = planes * (HW / vp);
+  int grid = (int)((total + kThreads - 1) / kThreads);
+  if (grid > 8 * sm_count()) grid = 8 * sm_count();
+#define CALL(V)                                                                                                   \
+  bn3_bwd_apply_kernel<V><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)du, (const __nv_bfloat16*)y1,            \
+      (const __nv_bfloat16*)y2, (const __nv_bfloat16*)y3, coef, (__nv_bfloat16*)dy1, (__nv_bfloat16*)dy2,           \
+      (__nv_bfloat16*)dy3, C, HW, planes)
+  SLAK_VP_DISPATCH(vp, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+}  // namespace blk
+}  // namespace slak

@@ -25,12 +25,38 @@ namespace tc {
 bool lk3_tc_supported(int N, int C, int H, int W, int KL);
 bool lk3_bwd_tc_supported(int N, int C, int H, int W, int KL);
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
-               int N, int C, int H, int W, int KL, cudaStream_t st);
+               int N, int C, int H, int W, int KL, float* stats, cudaStream_t st);
+int lk3_fwd_tc_splits(int N, int C, int H, int W);
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
                int N, int C, int H, int W, int KL, int KN, int flip, cudaStream_t st);
 size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL);
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
+}
+// block_fused.cu
+namespace blk {
+int bn3_stats_finalize(const float* part, int splits, double* sums_ws, int C, cudaStream_t st);
+int bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
+                     float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale, float* shift,
+                     float* mean, float* istd, cudaStream_t st);
+int bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean, const float* const* rvar,
+                    float eps, int C, float* scale, float* shift, cudaStream_t st);
+int bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean, const float* istd, int C,
+                     float* coef, float* dbnw, float* dbnb, cudaStream_t st);
+int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, const float* shift,
+                   const float* lnw, const float* lnb, float eps, void* xn, float* mu, float* rstd, int N, int C, int HW,
+                   cudaStream_t st);
+int residual_fwd(const float* x, const void* h2, const float* gamma, const float* dp, float* out, void* out_bf16,
+                 int N, int C, int HW, cudaStream_t st);
+int residual_bwd_parts(int N, int C, int HW);
+int residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2, float* dgamma_part,
+                 int N, int C, int HW, cudaStream_t st);
+int bn3_sum_ln_bwd_parts(int N, int C, int HW);
+int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
+                   const float* shift, const float* lnw, const float* mu, const float* rstd, void* du, float* part,
+                   int N, int C, int HW, cudaStream_t st);
+int bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef, void* dy1,
+                  void* dy2, void* dy3, int N, int C, int HW, cudaStream_t st);
 }
 // mask.cu
 int mask_apply(float* const* w_ptrs, const float* const* m_ptrs, float* const* e_ptrs,
@@ -119,7 +145,7 @@ SLAK_API int slak_lk_branches_fwd(const void* x, const float* w1, const float* w
   SLAK_REQUIRE((w3 == nullptr) == (y3 == nullptr), SLAK_ERR_BAD_ARG, "w3 and y3 must both be given or both be NULL");
   cudaStream_t st = (cudaStream_t)stream;
   if (w3 && slak_lk_branches_uses_tc(N, C, H, W, KL, KS, dtype))
-    return tc::lk3_fwd_tc(x, w1, w2, w3, y1, y2, y3, N, C, H, W, KL, st);
+    return tc::lk3_fwd_tc(x, w1, w2, w3, y1, y2, y3, N, C, H, W, KL, nullptr, st);
   rc = dwconv_simt_fwd(x, w1, y1, N, C, H, W, KL, KS, dtype, SLAK_F32, 0, st);
   if (rc) return rc;
   rc = dwconv_simt_fwd(x, w2, y2, N, C, H, W, KS, KL, dtype, SLAK_F32, 0, st);
@@ -163,6 +189,87 @@ SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const v
   SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE, "bwd_filter workspace too small: %zu < %zu",
                workspace_bytes, need);
   return tc::lk3_wgrad_tc(x, dy1, dy2, dy3, dw1, dw2, dw3, N, C, H, W, KL, workspace, (cudaStream_t)stream);
+}
+
+// ---- fused Block glue (block_fused.cu) --------------------------------------------------------
+SLAK_API size_t slak_block_conv_fwd_workspace(int N, int C, int H, int W) {
+  const int s = tc::lk3_fwd_tc_splits(N, C, H, W);
+  return s <= 0 ? 0 : (size_t)C * s * 6 * sizeof(float);
+}
+
+SLAK_API int slak_block_conv_fwd(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2,
+                                 void* y3, double* sums, void* workspace, size_t workspace_bytes, int N, int C, int H,
+                                 int W, int KL, void* stream) {
+  int rc = check_conv_args(x, w1, y1, N, C, H, W, KL, 5, SLAK_BF16, SLAK_F32);
+  if (rc) return rc;
+  SLAK_REQUIRE(w2 && w3 && y2 && y3 && sums, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(slak_lk_branches_uses_tc(N, C, H, W, KL, 5, SLAK_BF16), SLAK_ERR_UNSUPPORTED,
+               "slak_block_conv_fwd covers only the tensor-core shapes");
+  const size_t need = slak_block_conv_fwd_workspace(N, C, H, W);
+  SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = tc::lk3_fwd_tc(x, w1, w2, w3, y1, y2, y3, N, C, H, W, KL, (float*)workspace, st);
+  if (rc) return rc;
+  return blk::bn3_stats_finalize((const float*)workspace, tc::lk3_fwd_tc_splits(N, C, H, W), sums, C, st);
+}
+
+SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
+                                   float* const* rmean, float* const* rvar, float eps, float momentum, int C,
+                                   float* scale, float* shift, float* mean, float* istd, void* stream) {
+  SLAK_REQUIRE(sums && bnw && bnb && rmean && rvar && scale && shift && mean && istd && C > 0 && count > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  for (int i = 0; i < 3; ++i) SLAK_REQUIRE(bnw[i] && bnb[i], SLAK_ERR_BAD_ARG, "null BN parameter");
+  return blk::bn3_finalize_fwd(sums, count, bnw, bnb, rmean, rvar, eps, momentum, C, scale, shift, mean, istd, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean,
+                                  const float* const* rvar, float eps, int C, float* scale, float* shift, void* stream) {
+  SLAK_REQUIRE(bnw && bnb && rmean && rvar && scale && shift && C > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  for (int i = 0; i < 3; ++i) SLAK_REQUIRE(bnw[i] && bnb[i] && rmean[i] && rvar[i], SLAK_ERR_BAD_ARG, "null BN tensor");
+  return blk::bn3_eval_affine(bnw, bnb, rmean, rvar, eps, C, scale, shift, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, const float* shift,
+                                 const float* lnw, const float* lnb, float eps, void* xn, float* mu, float* rstd, int N,
+                                 int C, int HW, void* stream) {
+  SLAK_REQUIRE(y1 && y2 && y3 && scale && shift && lnw && lnb && xn && mu && rstd, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "non-positive size");
+  return blk::bn3_sum_ln_fwd(y1, y2, y3, scale, shift, lnw, lnb, eps, xn, mu, rstd, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_block_residual_fwd(const float* x, const void* h2, const float* gamma, const float* dp, float* out,
+                                     void* out_bf16, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(x && h2 && gamma && out && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::residual_fwd(x, h2, gamma, dp, out, out_bf16, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_block_residual_bwd_parts(int N, int C, int HW) { return blk::residual_bwd_parts(N, C, HW); }
+
+SLAK_API int slak_block_residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2,
+                                     float* dgamma_part, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(dout && h2 && gamma && dh2 && dgamma_part && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::residual_bwd(dout, h2, gamma, dp, dh2, dgamma_part, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_sum_ln_bwd_parts(int N, int C, int HW) { return blk::bn3_sum_ln_bwd_parts(N, C, HW); }
+
+SLAK_API int slak_bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
+                                 const float* shift, const float* lnw, const float* mu, const float* rstd, void* du,
+                                 float* part, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(dxn && y1 && y2 && y3 && scale && shift && lnw && mu && rstd && du && part, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "non-positive size");
+  return blk::bn3_sum_ln_bwd(dxn, y1, y2, y3, scale, shift, lnw, mu, rstd, du, part, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean, const float* istd,
+                                   int C, float* coef, float* dbnw, float* dbnb, void* stream) {
+  SLAK_REQUIRE(S && bnw && bnw[0] && bnw[1] && bnw[2] && mean && istd && coef && dbnw && dbnb && C > 0 && count > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::bn3_finalize_bwd(S, count, bnw, mean, istd, C, coef, dbnw, dbnb, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef,
+                                void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(du && y1 && y2 && y3 && coef && dy1 && dy2 && dy3 && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::bn3_bwd_apply(du, y1, y2, y3, coef, dy1, dy2, dy3, N, C, HW, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs,

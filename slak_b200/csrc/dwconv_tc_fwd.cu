@@ -57,6 +57,7 @@ struct FwdParams {
   int N, C, H, W, KL;
   int splits;            // CTAs per channel
   int units_per_c;       // ceil(N / PPU)
+  float* stats;          // optional [C][splits][6]: per-CTA (sum, sum of squares) of y1, y2, y3 (as rounded to bf16)
 };
 
 // cp.async loader of one unit (PPU planes of channel c) into a SWIZZLE_128B K-major tile
@@ -289,6 +290,8 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     const size_t plane_elems = (size_t)H * W;
     uint8_t* y1s = sm + Cfg::kOffY1;
     const int PR = W / E;                       // pieces per output row
+    float st_s[3] = {0.f, 0.f, 0.f}, st_q[3] = {0.f, 0.f, 0.f};   // BatchNorm statistics of this thread's elements
+    const bool want_stats = P.stats != nullptr;
     for (int i = 0; i < n_units; ++i) {
       const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
       const int n = PPU * (u_begin + i) + pl;
@@ -308,6 +311,13 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
 #pragma unroll
           for (int j = 0; j < T / E; ++j)          // static register indices
             if (j < PR) store_bf16_piece<E>(yo + j * E, v + j * E);
+          if (want_stats) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+              if (j < W) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))); s += f; q = fmaf(f, f, q); }
+            st_s[1 + br] += s; st_q[1 + br] += q;
+          }
         }
       }
       // ---- y1^T (cols 0..T-1): this thread holds column `row`(=q) for p = 0..T-1 -> staging[(pl,p)][q] ----
@@ -322,6 +332,13 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         const uint32_t off = r * 128 + ((((uint32_t)row >> 3) ^ (r & 7)) << 4) + (row & 7) * 2;
         *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(v[p]));
       }
+      if (want_stats && n < P.N && row < W) {       // this thread holds column q = row of y1 for p < H
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int p = 0; p < T; ++p)
+          if (p < H) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[p]))); s += f; q = fmaf(f, f, q); }
+        st_s[0] += s; st_q[0] += q;
+      }
       named_bar_sync(1, 128);
       if (ok) {
         __nv_bfloat16* yo = P.y1 + rbase;
@@ -334,6 +351,20 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
           }
       }
       named_bar_sync(1, 128);                     // staging free for the next unit
+    }
+    if (want_stats) {
+      // lanes -> warp -> the four epilogue warps, fixed order
+      float* red = reinterpret_cast<float*>(y1s);   // staging is free now
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float s = st_s[k], q = st_q[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if (lane == 0) { red[e * 6 + 2 * k] = s; red[e * 6 + 2 * k + 1] = q; }
+      }
+      named_bar_sync(1, 128);
+      if (e == 0 && lane < 6)
+        P.stats[((size_t)c * P.splits + split) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
     }
   }
 
@@ -423,8 +454,15 @@ static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
   return SLAK_OK;
 }
 
+int lk3_fwd_tc_splits(int N, int C, int H, int W) {
+  const TcShape s = tc_shape(H, W);
+  if (s.tile == 0) return 0;
+  const int ppu = 128 / s.tile;
+  return tc_pick_splits(C, (N + ppu - 1) / ppu);
+}
+
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
-               int N, int C, int H, int W, int KL, cudaStream_t st) {
+               int N, int C, int H, int W, int KL, float* stats, cudaStream_t st) {
   SLAK_REQUIRE(lk3_tc_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   SLAK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SLAK_ERR_BAD_ARG, "x must be 16-byte aligned");
   const TcShape s = tc_shape(H, W);
@@ -439,6 +477,7 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
   P.w1 = w1; P.w2 = w2; P.w3 = w3;
   P.y1 = (__nv_bfloat16*)y1; P.y2 = (__nv_bfloat16*)y2; P.y3 = (__nv_bfloat16*)y3;
   P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL;
+  P.stats = stats;
   if (s.tile == 64) return launch_fwd<64, 16, true>(map, P, st);
   if (s.tile == 32) {
     if (s.cb == 8) return launch_fwd<32, 8, false>(map, P, st);

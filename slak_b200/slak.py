@@ -17,10 +17,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import block as block_mod
 from . import ops
 from .dwconv import DepthWiseConv2dImplicitGEMM
 
 use_sync_bn = True
+FUSED_BLOCK = True      # route eligible Blocks through the fused node (slak_b200/block.py)
 
 
 # ---- small utilities the reference takes from timm (timm is not a dependency here) --------
@@ -215,6 +217,8 @@ class Block(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
+        if FUSED_BLOCK and block_mod.fused_block_supported(self, x):
+            return block_mod.fused_block_forward(self, x)       # one autograd node, see slak_b200/block.py
         shortcut = x
         if x.is_cuda and torch.is_autocast_enabled():
             # the depthwise branch is autocast-eligible here (the reference pins fp32 inputs to its

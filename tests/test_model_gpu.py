@@ -85,3 +85,66 @@ def test_block_bf16_autocast_tensor_core_path_vs_oracle():
     for n, p in blk.named_parameters():
         r = rel(p.grad, sd[n].grad)
         assert r < 6e-2, (n, r)
+
+
+@pytest.mark.parametrize("dim,hw,ks,dp", [(16, 56, 51, 0.0), (24, 28, 49, 0.3), (40, 14, 47, 0.0), (64, 7, 13, 0.0), (10, 20, 9, 0.0)])
+def test_fused_block_equals_module_by_module_path(dim, hw, ks, dp):
+    """FusedBlockFunction (fused BN/LN/residual kernels + tensor-core branches) against the same Block run
+    module by module (nn.BatchNorm2d, F.layer_norm, ...) under the same bf16 autocast."""
+    torch.manual_seed(1)
+    slak.use_sync_bn = False
+    blk = slak.Block(dim=dim, drop_path=dp, layer_scale_init_value=1.0, kernel_size=(ks, 5), Decom=True, bn=True)
+    for p in blk.parameters():
+        if p.dim() > 1:
+            torch.nn.init.normal_(p, std=0.05)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            torch.nn.init.uniform_(m.weight, 0.5, 1.5)
+            torch.nn.init.uniform_(m.bias, -0.5, 0.5)
+    blk = blk.to(DEV).train()
+    import copy
+    ref = copy.deepcopy(blk)
+    x = torch.randn(6, dim, hw, hw, device=DEV)
+    cot = torch.randn(6, dim, hw, hw, device=DEV)
+    outs = []
+    for fused, m in ((True, blk), (False, ref)):
+        slak.FUSED_BLOCK = fused
+        try:
+            torch.manual_seed(123)                      # same drop-path draw
+            xi = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = m(xi)
+            (y.float() * cot).sum().backward()
+            outs.append((y.detach().float(), xi.grad.float(), {n: p.grad.float() for n, p in m.named_parameters()},
+                         {n: b.clone().float() for n, b in m.named_buffers()}))
+        finally:
+            slak.FUSED_BLOCK = True
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+    (y0, dx0, g0, b0), (y1, dx1, g1, b1) = outs
+    assert y0.dtype == torch.float32
+    assert rel(y0, y1) < 2e-2, rel(y0, y1)
+    assert rel(dx0, dx1) < 4e-2, rel(dx0, dx1)
+    for n in g0:
+        assert rel(g0[n], g1[n]) < 6e-2, (n, rel(g0[n], g1[n]))
+    for n in b0:                                        # running statistics / num_batches_tracked
+        assert rel(b0[n], b1[n]) < 2e-2, (n, rel(b0[n], b1[n]))
+
+
+def test_fused_block_eval_mode_matches_module_path():
+    torch.manual_seed(2)
+    slak.use_sync_bn = False
+    blk = slak.Block(dim=32, drop_path=0.2, layer_scale_init_value=1.0, kernel_size=(49, 5), Decom=True, bn=True).to(DEV)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+    blk.eval()
+    x = torch.randn(5, 32, 28, 28, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y0 = blk(x)
+        slak.FUSED_BLOCK = False
+        try:
+            y1 = blk(x)
+        finally:
+            slak.FUSED_BLOCK = True
+    assert ((y0 - y1).abs().max() / y1.abs().max()).item() < 2e-2
