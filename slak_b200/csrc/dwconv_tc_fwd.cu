@@ -37,6 +37,9 @@ constexpr int kThreads = 320;
 template <int T> struct FwdCfg {
   static constexpr int PPU = 128 / T;            // planes per unit
   static constexpr int KSTEPS = T / 16;
+  static constexpr int UPS = 64 / T;             // 128-row groups per unit: group b fills the T-element band b of the rows
+  static constexpr int PLANES = PPU * UPS;       // planes per unit (2, 8, 32): ~12.5 KB of input for every tile class
+  static constexpr int NSTAGE = kStages;         // X units in flight
   static constexpr int kToep1 = 5 * T * 128;
   static constexpr int kToep23 = 5 * 2 * T * 128;
   static constexpr int kOffToep1 = 0;
@@ -45,9 +48,9 @@ template <int T> struct FwdCfg {
   static constexpr int kOffXT = kOffXN + kStages * kXSlot;
   static constexpr int kOffY1 = kOffXT + kXSlot;
   static constexpr int kOffBar = kOffY1 + kUnitBytes;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
-  static constexpr int kAccCols = 3 * T;
-  static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
+  static constexpr int kSmem = kOffBar + 1024 + 1024;
+  static constexpr int kAccCols = 3 * T * UPS;   // 192 for every class
+  static constexpr int kTmemCols = 512;
 };
 
 struct FwdParams {
@@ -56,44 +59,16 @@ struct FwdParams {
   __nv_bfloat16* y1; __nv_bfloat16* y2; __nv_bfloat16* y3;
   int N, C, H, W, KL;
   int splits;            // CTAs per channel
-  int units_per_c;       // ceil(N / PPU)
+  int units_per_c;       // ceil(N / PLANES)
   float* stats;          // optional [C][splits][6]: per-CTA (sum, sum of squares) of y1, y2, y3 (as rounded to bf16)
 };
-
-// cp.async loader of one unit (PPU planes of channel c) into a SWIZZLE_128B K-major tile
-template <int T, int CB>
-__device__ __forceinline__ void load_unit_pieces(const __nv_bfloat16* __restrict__ x, uint32_t tile, int n0, int c,
-                                                 int N, int C, int H, int W, int lane) {
-  constexpr int PPU = 128 / T;
-  const int PR = (W * 2) / CB;               // pieces per row
-  const int per_plane = H * PR;
-  const size_t plane_bytes = (size_t)H * W * 2;
-  for (int pl = 0; pl < PPU; ++pl) {
-    const int n = n0 + pl;
-    if (n >= N) break;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + ((size_t)n * C + c) * plane_bytes;
-    for (int e = lane; e < per_plane; e += 32) {
-      const int p = e / PR, j = e - p * PR;
-      const int row = pl * T + p;
-      const int b = j * CB;
-      const uint32_t dst = tile + row * 128 + ((((b >> 4) ^ (row & 7))) << 4) + (b & 15);
-      const uint8_t* s = src + (size_t)p * W * 2 + b;
-      if constexpr (CB >= 4) {
-        cp_async<CB>(dst, s);
-      } else {
-        const uint16_t val = *reinterpret_cast<const uint16_t*>(s);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "h"(val) : "memory");
-      }
-    }
-  }
-}
 
 template <int T, int CB, bool TMA>
 __global__ void __launch_bounds__(kThreads, 1)
 lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   using Cfg = FwdCfg<T>;
-  constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2;
-  constexpr int kNumLoaders = TMA ? 1 : kStages;
+  constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2, UPS = Cfg::UPS, NSTAGE = Cfg::NSTAGE;
+  constexpr int kNumLoaders = TMA ? 1 : 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -107,14 +82,17 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   const int n_units = u_end - u_begin;
   const int KL = P.KL, pad = KL / 2, H = P.H, W = P.W;
 
-  constexpr int B_XN_FULL = 0, B_XN_EMPTY = kStages, B_XT_FULL = 2 * kStages, B_XT_EMPTY = B_XT_FULL + 1,
+  constexpr int PLANES = Cfg::PLANES;
+  constexpr int B_XN_FULL = 0, B_XN_EMPTY = NSTAGE, B_XT_FULL = 2 * NSTAGE, B_XT_EMPTY = B_XT_FULL + 1,
                 B_ACC_FULL = B_XT_EMPTY + 1, B_ACC_EMPTY = B_ACC_FULL + kAccBufs;
   const uint32_t bar0 = base + Cfg::kOffBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cfg::kOffBar + 192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cfg::kOffBar + 768);
+  // a unit = one 128-row x 64-column slot: row group pl (T rows) x column band b (T columns) holds plane b*PPU + pl
+  auto XN_ADDR = [&](int s) { return base + Cfg::kOffXN + s * kXSlot + kPad; };
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(BAR(B_XN_FULL + s), 1);                          // TMA expect_tx arrive / loader lane 0
       mbar_init(BAR(B_XN_EMPTY + s), 1 + kNumTransposerWarps);   // MMA commit + transposers done reading
     }
@@ -190,10 +168,10 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       // ================= TMA producer (T = 64: two planes per unit) =================
       if (elect_one()) {
         for (int i = 0; i < n_units; ++i) {
-          const int st = i % kStages, ph = (i / kStages) & 1;
+          const int st = i % NSTAGE, ph = (i / NSTAGE) & 1;
           mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
-          const int n0 = PPU * (u_begin + i);
-          const uint32_t dst = base + Cfg::kOffXN + st * kXSlot + kPad;
+          const int n0 = PLANES * (u_begin + i);
+          const uint32_t dst = XN_ADDR(st);
           mbar_expect_tx(BAR(B_XN_FULL + st), kUnitBytes);
 #pragma unroll
           for (int pl = 0; pl < PPU; ++pl)
@@ -201,18 +179,25 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         }
       }
     } else {
-      // ================= cp.async loaders: loader j owns stage j, one unit in flight each =============
+      // ================= cp.async loaders: loader j owns slot j (one unit = PLANES planes in flight each) ====
       const int lj = (warp == 0) ? 0 : (warp - 7);           // 0, 1, 2
+      PieceMap<CB> pm;
+      pm.init(H, W, lane);
+      const size_t plane_bytes = (size_t)H * W * 2;
       for (int i = lj; i < n_units; i += kNumLoaders) {
-        const int st = lj;                                    // == i % kStages
-        const int ph = (i / kStages) & 1;
-        mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
-        load_unit_pieces<T, CB>(P.x, base + Cfg::kOffXN + st * kXSlot + kPad, PPU * (u_begin + i), c, P.N, P.C, H, W, lane);
+        const int s = lj, ph = (i / NSTAGE) & 1;              // lj == i % NSTAGE
+        mbar_wait(BAR(B_XN_EMPTY + s), ph ^ 1);
+        const uint32_t tile = XN_ADDR(s);
+        const int n0 = PLANES * (u_begin + i);
+        for (int q = 0; q < PLANES; ++q)
+          if (n0 + q < P.N)
+            load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.x) + ((size_t)(n0 + q) * P.C + c) * plane_bytes,
+                                 tile, (q % PPU) * T, (q / PPU) * (T / 8), lane);
         cp_async_commit();
         cp_async_wait_all();
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_XN_FULL + st));
+        if (lane == 0) mbar_arrive(BAR(B_XN_FULL + s));
       }
     }
   } else if (warp == 1) {
@@ -221,34 +206,37 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       constexpr uint32_t idesc23 = umma_idesc_bf16(128, 2 * T);
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, T);
       for (int i = 0; i < n_units; ++i) {
-        const int st = i % kStages, ph = (i / kStages) & 1;
+        const int st = i % NSTAGE, ph = (i / NSTAGE) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
         mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);   // epilogue drained this accumulator buffer
         mbar_wait(BAR(B_XN_FULL + st), ph);          // X landed
         tc_fence_after();
-        const uint32_t xn = base + Cfg::kOffXN + st * kXSlot + kPad;
+        const uint32_t xn = XN_ADDR(st);
         const uint32_t xt = base + Cfg::kOffXT + kPad;
-        const uint32_t d1 = tmem + ab * Cfg::kAccCols;
-        const uint32_t d23 = d1 + T;
+        const uint32_t acc = tmem + ab * Cfg::kAccCols;
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
+        for (int g = 0; g < UPS; ++g)                // column band g = row-group set g
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            const uint32_t a = xn + (r - 2) * 128 + k * 32;
-            const uint32_t b = base + Cfg::kOffToep23 + r * (2 * T * 128) + k * 32;
-            umma_bf16(d23, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc23, (r | k) != 0);
-          }
+          for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint32_t a = xn + (r - 2) * 128 + g * (T * 2) + k * 32;
+              const uint32_t b = base + Cfg::kOffToep23 + r * (2 * T * 128) + k * 32;
+              umma_bf16(acc + g * 3 * T + T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc23, (r | k) != 0);
+            }
         umma_commit(BAR(B_XN_EMPTY + st));           // X slot free (with the transposers' arrivals)
         mbar_wait(BAR(B_XT_FULL), i & 1);            // X^T written
         tc_fence_after();
 #pragma unroll
-        for (int s = 0; s < 5; ++s)
+        for (int g = 0; g < UPS; ++g)
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            const uint32_t a = xt + (s - 2) * 128 + k * 32;
-            const uint32_t b = base + Cfg::kOffToep1 + s * (T * 128) + k * 32;
-            umma_bf16(d1, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc1, (s | k) != 0);
-          }
+          for (int s = 0; s < 5; ++s)
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint32_t a = xt + (s - 2) * 128 + g * (T * 2) + k * 32;
+              const uint32_t b = base + Cfg::kOffToep1 + s * (T * 128) + k * 32;
+              umma_bf16(acc + g * 3 * T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc1, (s | k) != 0);
+            }
         umma_commit(BAR(B_XT_EMPTY));                // X^T slot free
         umma_commit(BAR(B_ACC_FULL + ab));           // accumulators ready
       }
@@ -259,18 +247,19 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     const int m = lane >> 3, kk = lane & 7;     // matrix id within the x4, row within the 8x8 block
     constexpr int NB = T / 8;                   // blocks per plane edge
     for (int i = 0; i < n_units; ++i) {
-      const int st = i % kStages, ph = (i / kStages) & 1;
+      const int st = i % NSTAGE, ph = (i / NSTAGE) & 1;
       mbar_wait(BAR(B_XN_FULL + st), ph);       // X landed
       mbar_wait(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed
-      const uint32_t xn = base + Cfg::kOffXN + st * kXSlot + kPad;
+      const uint32_t xn = XN_ADDR(st);
       const uint32_t xt = base + Cfg::kOffXT + kPad;
 #pragma unroll 4
-      for (int it = tw; it < T / 2; it += kNumTransposerWarps) {
+      for (int it = tw; it < 32; it += kNumTransposerWarps) {       // 128 8x8 blocks: every T x T block in place
         const int blk = 4 * it + m;
-        const int pl = blk / (NB * NB), rem = blk - pl * (NB * NB);
+        const int g = blk / (2 * T), rem0 = blk - g * (2 * T);      // column band
+        const int pl = rem0 / (NB * NB), rem = rem0 - pl * (NB * NB);
         const int bi = rem / NB, bj = rem - bi * NB;
-        const uint32_t src = xn + (pl * T + 8 * bi + kk) * 128 + ((bj ^ kk) << 4);
-        const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + ((bi ^ kk) << 4);
+        const uint32_t src = xn + (pl * T + 8 * bi + kk) * 128 + (((g * NB + bj) ^ kk) << 4);
+        const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + (((g * NB + bi) ^ kk) << 4);
         uint32_t r0, r1, r2, r3;
         ldmatrix_x4_trans(src, r0, r1, r2, r3);
         stmatrix_x4(dst, r0, r1, r2, r3);
@@ -294,61 +283,68 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     const bool want_stats = P.stats != nullptr;
     for (int i = 0; i < n_units; ++i) {
       const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
-      const int n = PPU * (u_begin + i) + pl;
-      const bool ok = (n < P.N) && (row < H);
-      const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
       mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
-      const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * Cfg::kAccCols;
       uint32_t v[T];
-      // ---- y2 (cols T..2T-1 of the buffer) and y3 (cols 2T..3T-1): natural orientation ----
 #pragma unroll
-      for (int br = 0; br < 2; ++br) {
-        tmem_ld_cols<T>(t0 + T + br * T, v);
-        tmem_ld_wait();
-        if (ok) {
-          __nv_bfloat16* yo = (br == 0 ? P.y2 : P.y3) + rbase;
+      for (int g = 0; g < UPS; ++g) {               // row-group set / column band g: plane g*PPU + pl
+        const int n = PLANES * (u_begin + i) + g * PPU + pl;
+        const bool ok = (n < P.N) && (row < H);
+        const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
+        const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * Cfg::kAccCols + g * 3 * T;
+        // ---- y2 (cols T..2T-1 of the group) and y3 (cols 2T..3T-1): natural orientation ----
 #pragma unroll
-          for (int j = 0; j < T / E; ++j)          // static register indices
-            if (j < PR) store_bf16_piece<E>(yo + j * E, v + j * E);
-          if (want_stats) {
-            float s = 0.f, q = 0.f;
+        for (int br = 0; br < 2; ++br) {
+          tmem_ld_cols<T>(t0 + T + br * T, v);
+          tmem_ld_wait();
+          if (ok) {
+            __nv_bfloat16* yo = (br == 0 ? P.y2 : P.y3) + rbase;
 #pragma unroll
-            for (int j = 0; j < T; ++j)
-              if (j < W) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))); s += f; q = fmaf(f, f, q); }
-            st_s[1 + br] += s; st_q[1 + br] += q;
+            for (int j = 0; j < T / E; ++j)          // static register indices
+              if (j < PR) store_bf16_piece<E>(yo + j * E, v + j * E);
+            if (want_stats) {
+              float s = 0.f, q = 0.f;
+#pragma unroll
+              for (int j = 0; j < T; ++j)
+                if (j < W) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))); s += f; q = fmaf(f, f, q); }
+              st_s[1 + br] += s; st_q[1 + br] += q;
+            }
           }
         }
+        // ---- y1^T (cols 0..T-1): this thread holds column `row`(=q) for p = 0..T-1 -> staging[(pl,p)][band g, q] ----
+        tmem_ld_cols<T>(t0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int p = 0; p < T; ++p) {
+          const uint32_t r = (uint32_t)(pl * T + p);
+          const uint32_t off = r * 128 + (((uint32_t)(g * (T / 8)) + ((uint32_t)row >> 3)) ^ (r & 7)) * 16 + (row & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(v[p]));
+        }
+        if (want_stats && n < P.N && row < W) {       // this thread holds column q = row of y1 for p < H
+          float s = 0.f, q = 0.f;
+#pragma unroll
+          for (int p = 0; p < T; ++p)
+            if (p < H) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[p]))); s += f; q = fmaf(f, f, q); }
+          st_s[0] += s; st_q[0] += q;
+        }
       }
-      // ---- y1^T (cols 0..T-1): this thread holds column `row`(=q) for p = 0..T-1 -> staging[(pl,p)][q] ----
-      tmem_ld_cols<T>(t0, v);
-      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));   // accumulators drained
-#pragma unroll
-      for (int p = 0; p < T; ++p) {
-        const uint32_t r = (uint32_t)(pl * T + p);
-        const uint32_t off = r * 128 + ((((uint32_t)row >> 3) ^ (r & 7)) << 4) + (row & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(v[p]));
-      }
-      if (want_stats && n < P.N && row < W) {       // this thread holds column q = row of y1 for p < H
-        float s = 0.f, q = 0.f;
-#pragma unroll
-        for (int p = 0; p < T; ++p)
-          if (p < H) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[p]))); s += f; q = fmaf(f, f, q); }
-        st_s[0] += s; st_q[0] += q;
-      }
       named_bar_sync(1, 128);
-      if (ok) {
-        __nv_bfloat16* yo = P.y1 + rbase;
-        const uint32_t r = (uint32_t)(pl * T + row);
 #pragma unroll
-        for (int j = 0; j < T / E; ++j)
-          if (j < PR) {
-            const uint32_t b = j * CB;
-            copy_piece<E>(yo + j * E, y1s + r * 128 + (((b >> 4) ^ (r & 7)) << 4) + (b & 15));
-          }
+      for (int g = 0; g < UPS; ++g) {
+        const int n = PLANES * (u_begin + i) + g * PPU + pl;
+        if ((n < P.N) && (row < H)) {
+          __nv_bfloat16* yo = P.y1 + ((size_t)n * P.C + c) * plane_elems + (size_t)row * W;
+          const uint32_t r = (uint32_t)(pl * T + row);
+#pragma unroll
+          for (int j = 0; j < T / E; ++j)
+            if (j < PR) {
+              const uint32_t b = j * CB;
+              copy_piece<E>(yo + j * E, y1s + r * 128 + ((((uint32_t)(g * (T / 8)) + (b >> 4)) ^ (r & 7)) << 4) + (b & 15));
+            }
+        }
       }
       named_bar_sync(1, 128);                     // staging free for the next unit
     }
@@ -431,7 +427,7 @@ bool lk3_tc_supported(int N, int C, int H, int W, int KL) {
 int tc_pick_splits(int C, int units) {
   const int sms = sm_count();
   int best = 1; double best_eff = 0.0;
-  const int max_s = units >= 8 ? units / 4 : 1;
+  const int max_s = units >= 4 ? units / 2 : 1;
   for (int s = 1; s <= max_s && s <= 64; ++s) {
     const long long ctas = (long long)C * s;
     const long long waves = (ctas + sms - 1) / sms;
@@ -445,7 +441,7 @@ int tc_pick_splits(int C, int units) {
 template <int T, int CB, bool TMA>
 static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
   using Cfg = FwdCfg<T>;
-  P.units_per_c = (P.N + Cfg::PPU - 1) / Cfg::PPU;
+  P.units_per_c = (P.N + Cfg::PLANES - 1) / Cfg::PLANES;
   P.splits = tc_pick_splits(P.C, P.units_per_c);
   auto kern = lk3_fwd_tc_kernel<T, CB, TMA>;
   SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -457,8 +453,8 @@ static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
 int lk3_fwd_tc_splits(int N, int C, int H, int W) {
   const TcShape s = tc_shape(H, W);
   if (s.tile == 0) return 0;
-  const int ppu = 128 / s.tile;
-  return tc_pick_splits(C, (N + ppu - 1) / ppu);
+  const int planes = (128 / s.tile) * (64 / s.tile);
+  return tc_pick_splits(C, (N + planes - 1) / planes);
 }
 
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,

@@ -189,6 +189,75 @@ __device__ __forceinline__ void copy_piece(__nv_bfloat16* dst, const uint8_t* sr
   else if constexpr (E == 2) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
   else *dst = *reinterpret_cast<const __nv_bfloat16*>(src);
 }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- plane loader for the small tile classes ---------------------------------------------------
+// A plane (H x W bf16, contiguous in HBM) is copied in CB-byte pieces into a T x T block of a
+// SWIZZLE_128B tile: block rows [row0, row0+H), 16-byte chunk columns [cb0, cb0 + T/8).  The piece ->
+// (source offset, row, byte) map is the same for every plane, so each lane precomputes its pieces once.
+template <int CB>
+struct PieceMap {
+  static constexpr int kMax = 8;
+  int count;                 // pieces of this lane (<= kMax) or -1: too many, compute on the fly
+  int per_plane, PR, W;
+  uint32_t soff[kMax];       // source byte offset inside the plane
+  uint32_t pb[kMax];         // (row << 8) | byte offset inside the row
+  __device__ __forceinline__ void init(int H, int W_, int lane) {
+    W = W_;
+    PR = (W * 2) / CB;
+    per_plane = H * PR;
+    count = 0;
+    if (per_plane > kMax * 32) { count = -1; return; }
+#pragma unroll
+    for (int k = 0; k < kMax; ++k) {
+      const int e = lane + 32 * k;
+      soff[k] = 0; pb[k] = 0;
+      if (e < per_plane) {
+        const int p = e / PR, j = e - p * PR;
+        soff[k] = (uint32_t)(p * W * 2 + j * CB);
+        pb[k] = ((uint32_t)p << 8) | (uint32_t)(j * CB);
+        count = k + 1;
+      }
+    }
+  }
+};
+
+template <int CB>
+__device__ __forceinline__ void copy_piece_g2s(uint32_t dst, const uint8_t* src) {
+  if constexpr (CB >= 4) {
+    cp_async<CB>(dst, src);
+  } else {
+    const uint16_t val = *reinterpret_cast<const uint16_t*>(src);
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "h"(val) : "memory");
+  }
+}
+
+// copy one plane into the tile block at (row0, chunk column cb0)
+template <int CB>
+__device__ __forceinline__ void load_plane_block(const PieceMap<CB>& pm, const uint8_t* __restrict__ src, uint32_t tile,
+                                                 int row0, int cb0, int lane) {
+  if (pm.count >= 0) {
+#pragma unroll
+    for (int k = 0; k < PieceMap<CB>::kMax; ++k) {
+      if (k < pm.count && (lane + 32 * k) < pm.per_plane) {
+        const uint32_t p = pm.pb[k] >> 8, b = pm.pb[k] & 0xff;
+        const uint32_t row = (uint32_t)row0 + p;
+        const uint32_t dst = tile + row * 128 + ((((uint32_t)cb0 + (b >> 4)) ^ (row & 7)) << 4) + (b & 15);
+        copy_piece_g2s<CB>(dst, src + pm.soff[k]);
+      }
+    }
+  } else {
+    for (int e = lane; e < pm.per_plane; e += 32) {
+      const int p = e / pm.PR, j = e - p * pm.PR;
+      const uint32_t b = (uint32_t)(j * CB);
+      const uint32_t row = (uint32_t)(row0 + p);
+      const uint32_t dst = tile + row * 128 + ((((uint32_t)cb0 + (b >> 4)) ^ (row & 7)) << 4) + (b & 15);
+      copy_piece_g2s<CB>(dst, src + (size_t)p * pm.W * 2 + b);
+    }
+  }
+}
+
 template <int NC>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
   if constexpr (NC == 64) { tmem_ld32(taddr, v); tmem_ld32(taddr + 32, v + 32); }
