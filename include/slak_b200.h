@@ -115,6 +115,11 @@ SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const v
                                        const float* w1, const float* w2, const float* w3,
                                        void* dx, void* tmp, int N, int C, int H, int W,
                                        int KL, int KS, int dtype, void* stream);
+/* the same with an fp32 result: dx = addend (fp32 [N,C,H,W], may be NULL) + the three bf16 dgrads; used by the
+ * Block backward where `addend` is the shortcut gradient */
+SLAK_API int slak_lk_branches_bwd_data_f32(const void* dy1, const void* dy2, const void* dy3, const float* w1,
+                                           const float* w2, const float* w3, const float* addend, float* dx,
+                                           void* tmp, int N, int C, int H, int W, int KL, int KS, void* stream);
 SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS);
 SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const void* dy2, const void* dy3,
                                          float* dw1, float* dw2, float* dw3, int N, int C, int H, int W,
@@ -133,7 +138,8 @@ SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const v
  *   bn3_eval_affine   : the same affine from running statistics (eval mode)
  *   bn3_sum_ln_fwd    : xn = LayerNorm_C(sum_i scale_i*y_i + shift), per-pixel mu/rstd saved
  *   block_residual_fwd: out = x + dp[n]*gamma[c]*h2 (dp may be NULL = 1; out_bf16 optional copy)
- *   block_residual_bwd: dh2 = dout*gamma*dp ; dgamma_part [parts][C] partial sums of dout*h2*dp
+ *   block_residual_bwd: dh2 = dout*gamma*dp ; dgamma_part [parts][2][C] partial sums of dout*h2*dp and of dh2
+ *   gelu_bwd_bias     : dh = da * gelu'(h) (exact erf GELU) over [rows][K] bf16, part [parts][K] column sums of dh
  *   bn3_sum_ln_bwd    : du = LayerNorm backward of dxn ; part [parts][6][C] = dlnw, dlnb, sum du, sum du*y_i
  *   bn3_finalize_bwd  : from GLOBAL S[4][C] -> coef[9][C] (dy_i = A_i*du + B_i*y_i + C_i), dbnw/dbnb [3][C]
  *   bn3_bwd_apply     : dy1, dy2, dy3 in one pass
@@ -159,6 +165,9 @@ SLAK_API int slak_block_residual_fwd(const float* x, const void* h2, const float
 SLAK_API int slak_block_residual_bwd_parts(int N, int C, int HW);
 SLAK_API int slak_block_residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp,
                                      void* dh2, float* dgamma_part, int N, int C, int HW, void* stream);
+SLAK_API int slak_gelu_bwd_bias_parts(int64_t rows, int K);
+SLAK_API int slak_gelu_bwd_bias(const void* da, const void* h, void* dh, float* part, int64_t rows, int K,
+                                void* stream);
 SLAK_API int slak_bn3_sum_ln_bwd_parts(int N, int C, int HW);
 SLAK_API int slak_bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3,
                                  const float* scale, const float* shift, const float* lnw, const float* mu,

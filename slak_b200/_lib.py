@@ -35,6 +35,7 @@ SIGNATURES = {
     "slak_lk_branches_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "slak_lk_branches_bwd_uses_tc": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "slak_lk_branches_bwd_data": (_i, [_vp] * 8 + [_i] * 7 + [_vp]),
+    "slak_lk_branches_bwd_data_f32": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
     "slak_lk_branches_bwd_filter_workspace": (_sz, [_i] * 6),
     "slak_lk_branches_bwd_filter": (_i, [_vp] * 7 + [_i] * 7 + [_vp, _sz, _vp]),
     "slak_block_conv_fwd_workspace": (_sz, [_i] * 4),
@@ -45,6 +46,8 @@ SIGNATURES = {
     "slak_block_residual_fwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
     "slak_block_residual_bwd_parts": (_i, [_i] * 3),
     "slak_block_residual_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
+    "slak_gelu_bwd_bias_parts": (_i, [_i64, _i]),
+    "slak_gelu_bwd_bias": (_i, [_vp] * 4 + [_i64, _i, _vp]),
     "slak_bn3_sum_ln_bwd_parts": (_i, [_i] * 3),
     "slak_bn3_sum_ln_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_vp]),
     "slak_bn3_finalize_bwd": (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

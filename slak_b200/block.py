@@ -100,7 +100,6 @@ class FusedBlockFunction(torch.autograd.Function):
         h = torch.addmm(b1.to(bf16), xf, W1b.t())
         a = F.gelu(h)
         h2 = torch.addmm(b2.to(bf16), a, W2b.t())
-        del a
         out = torch.empty_like(x)
         _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), None, N, C, HW, st),
             "slak_block_residual_fwd")
@@ -109,12 +108,12 @@ class FusedBlockFunction(torch.autograd.Function):
         ctx.count = count
         ctx.dims = (N, C, H, W, KL)
         ctx.save_for_backward(xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd,
-                              xn, h, h2, W1b, W2b, gamma, dp)
+                              xn, h, a, h2, W1b, W2b, gamma, dp)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd, xn, h, h2, W1b, W2b,
+        (xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd, xn, h, a, h2, W1b, W2b,
          gamma, dp) = ctx.saved_tensors
         cfg = ctx.cfg
         if not cfg["training"]:
@@ -131,23 +130,24 @@ class FusedBlockFunction(torch.autograd.Function):
         # ---- residual / gamma ---------------------------------------------------------------------
         parts = lib.slak_block_residual_bwd_parts(N, C, HW)
         dh2 = torch.empty((N * HW, C), dtype=bf16, device=dev)
-        dgp = torch.empty((parts, C), dtype=torch.float32, device=dev)
+        dgp = torch.empty((parts, 2, C), dtype=torch.float32, device=dev)
         _ck(lib.slak_block_residual_bwd(_p(dout), _p(h2), _p(gamma), _p(dp), _p(dh2), _p(dgp), N, C, HW, st),
             "slak_block_residual_bwd")
-        dgamma = dgp.sum(0)
-        # ---- MLP backward (cuBLAS) -----------------------------------------------------------------
-        a = F.gelu(h)
+        dg2 = dgp.sum(0)
+        dgamma, db2 = dg2[0], dg2[1]
+        # ---- MLP backward (cuBLAS GEMMs + one fused GELU'/bias-gradient pass) -----------------------------
         dW2 = torch.mm(dh2.t(), a).float()
-        db2 = dh2.sum(0, dtype=torch.float32)
         da = torch.mm(dh2, W2b)
-        del a
-        dh = torch.ops.aten.gelu_backward(da, h)
-        del da
+        K = h.shape[1]
+        parts = lib.slak_gelu_bwd_bias_parts(N * HW, K)
+        hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
+        _ck(lib.slak_gelu_bwd_bias(_p(da), _p(h), _p(da), _p(hp), N * HW, K, st), "slak_gelu_bwd_bias")   # in place
+        dh = da
+        db1 = hp.sum(0)
         xf = xn.view(N * HW, C)
         dW1 = torch.mm(dh.t(), xf).float()
-        db1 = dh.sum(0, dtype=torch.float32)
         dxn = torch.mm(dh, W1b)
-        del dh
+        del dh, da
         # ---- LayerNorm backward + BatchNorm reductions ------------------------------------------------
         parts = lib.slak_bn3_sum_ln_bwd_parts(N, C, HW)
         du = torch.empty_like(xb)
@@ -172,9 +172,12 @@ class FusedBlockFunction(torch.autograd.Function):
         del du
         ops._count(4)
         # ---- depthwise branches: fused tensor-core dgrad / wgrad ------------------------------------------
-        dxc = ops.lk_branches_backward_data(dy1, dy2, dy3, w1, w2, w3)
+        dx = torch.empty_like(dout)               # shortcut + branch gradient, fp32, written by the dgrad epilogue
+        tmp = torch.empty_like(dy3)
+        _ck(lib.slak_lk_branches_bwd_data_f32(_p(dy1), _p(dy2), _p(dy3), _p(w1), _p(w2), _p(w3), _p(dout), _p(dx),
+                                              _p(tmp), N, C, H, W, KL, 5, st), "slak_lk_branches_bwd_data_f32")
+        ops._count(2)
         dw1, dw2, dw3 = ops.lk_branches_backward_filter(xb, dy1, dy2, dy3, KL, 5)
-        dx = dout + dxc                           # shortcut + branch gradient, fp32
         return (dx, dw1, dw2, dw3, dbnw[0], dbnw[1], dbnw[2], dbnb[0], dbnb[1], dbnb[2], dlnw, dlnb,
                 dW1, db1, dW2, db2, dgamma, None, None)
 

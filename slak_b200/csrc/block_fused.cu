@@ -189,13 +189,14 @@ template <int VP>
 __global__ void __launch_bounds__(kThreads)
 residual_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h2,
                     const float* __restrict__ gamma, const float* __restrict__ dp,
-                    __nv_bfloat16* __restrict__ dh2, float* __restrict__ dgamma_part /*[grid][C]*/, Geo g) {
+                    __nv_bfloat16* __restrict__ dh2, float* __restrict__ dgamma_part /*[grid][2][C]: dgamma, db2*/, Geo g) {
   extern __shared__ float tile[];
-  float* acc = tile + (size_t)g.C * g.pitch;   // [kWarps][C]
+  float* acc = tile + (size_t)g.C * g.pitch;   // [kWarps][C] dgamma
+  float* acc2 = acc + kWarps * g.C;            // [kWarps][C] column sums of dh2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
   const int vec_per_row = PIX / VP;
-  for (int i = tid; i < kWarps * C; i += kThreads) acc[i] = 0.f;
+  for (int i = tid; i < 2 * kWarps * C; i += kThreads) acc[i] = 0.f;
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
     const int npix = min(PIX, HW - p0);
@@ -227,25 +228,80 @@ residual_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restr
         for (int c = 2 * lane; c < C; c += 64) {
           const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hp + c));
           const float g0 = tile[c * pitch + j] * dps, g1 = tile[(c + 1) * pitch + j] * dps;
-          *reinterpret_cast<__nv_bfloat162*>(dp_out + c) = __floats2bfloat162_rn(g0 * gamma[c], g1 * gamma[c + 1]);
+          const __nv_bfloat162 d2 = __floats2bfloat162_rn(g0 * gamma[c], g1 * gamma[c + 1]);
+          *reinterpret_cast<__nv_bfloat162*>(dp_out + c) = d2;
+          const float2 d2f = __bfloat1622float2(d2);
           acc[warp * C + c] += g0 * h.x;
           acc[warp * C + c + 1] += g1 * h.y;
+          acc2[warp * C + c] += d2f.x;
+          acc2[warp * C + c + 1] += d2f.y;
         }
       } else {
         for (int c = lane; c < C; c += 32) {
           const float g0 = tile[c * pitch + j] * dps;
-          dp_out[c] = __float2bfloat16_rn(g0 * gamma[c]);
+          const __nv_bfloat16 d1 = __float2bfloat16_rn(g0 * gamma[c]);
+          dp_out[c] = d1;
           acc[warp * C + c] += g0 * bf(hp[c]);
+          acc2[warp * C + c] += bf(d1);
         }
       }
     }
   }
   __syncthreads();
   for (int c = tid; c < C; c += kThreads) {
-    float s = 0.f;
+    float s = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += acc[w * C + c];
-    dgamma_part[(size_t)blockIdx.x * C + c] = s;
+    for (int w = 0; w < kWarps; ++w) { s += acc[w * C + c]; s2 += acc2[w * C + c]; }
+    dgamma_part[(size_t)blockIdx.x * 2 * C + c] = s;
+    dgamma_part[(size_t)blockIdx.x * 2 * C + C + c] = s2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MLP backward glue: dh = da * gelu'(h) (exact erf GELU), plus per-CTA column sums of dh
+// (bias gradient of pwconv1).  da, h, dh: [rows][K] bf16 row-major, K % 8 == 0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__global__ void __launch_bounds__(kThreads)
+gelu_bwd_bias_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ h,
+                     __nv_bfloat16* __restrict__ dh, float* __restrict__ part /*[grid][K]*/, long long rows, int K,
+                     int rows_per_cta) {
+  extern __shared__ float red[];               // [rsub][K]
+  const int nv = K / 8;
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  const int rsubs = nv >= kThreads ? 1 : kThreads / nv;
+  for (int v0 = 0; v0 < nv; v0 += kThreads) {
+    const int vec = v0 + (nv >= kThreads ? tid : tid % nv);
+    const int rsub = nv >= kThreads ? 0 : tid / nv;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    if (vec < nv && rsub < rsubs) {
+      for (long long r = r0 + rsub; r < r1; r += rsubs) {
+        const size_t off = (size_t)r * K + (size_t)vec * 8;
+        float a[8], x[8], o[8];
+        ld_bf16<8>(da + off, a); ld_bf16<8>(h + off, x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = a[k] * gelu_grad(x[k]);
+        st_bf16<8>(dh + off, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += __bfloat162float(__float2bfloat16_rn(o[k]));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[(size_t)rsub * K + vec * 8 + k] = s[k];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < K; c += kThreads) {
+    float t = 0.f;
+    for (int rs = 0; rs < rsubs; ++rs) t += red[(size_t)rs * K + c];
+    part[(size_t)blockIdx.x * K + c] = t;
   }
 }
 
@@ -264,9 +320,17 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
   const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
   float* accw = tile + (size_t)C * pitch;      // [kWarps][2][C]  dlnw, dlnb per warp
   float* accs = accw + kWarps * 2 * C;         // [4][C]          S0..S3 (each channel owned by one warp)
+  float* lnw_s = accs + 4 * C;                 // [C]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vec_per_row = PIX / VP;
   for (int i = tid; i < kWarps * 2 * C + 4 * C; i += kThreads) accw[i] = 0.f;
+  for (int i = tid; i < C; i += kThreads) lnw_s[i] = lnw[i];
+  // register path: each lane owns channel pairs (2*lane + 64k, +1), k < KM, for every pixel its warp visits
+  constexpr int KM = 12;
+  const bool regpath = ((C & 1) == 0) && (C <= 64 * KM);
+  float aw0[KM], aw1[KM], ab0[KM], ab1[KM];
+#pragma unroll
+  for (int k = 0; k < KM; ++k) { aw0[k] = aw1[k] = ab0[k] = ab1[k] = 0.f; }
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
     const int npix = min(PIX, HW - p0);
@@ -291,6 +355,36 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
       const float m = mu[pix], r = rstd[pix];
       const __nv_bfloat16* gp = dxn + pix * C;
       float s1 = 0.f, s2 = 0.f;
+      if (regpath) {
+        uint32_t graw[KM];
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+          const int c = 2 * lane + 64 * k;
+          graw[k] = 0u;
+          if (c < C) {
+            graw[k] = *reinterpret_cast<const uint32_t*>(gp + c);
+            const float2 gx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&graw[k]));
+            const float xh0 = (tile[c * pitch + j] - m) * r, xh1 = (tile[(c + 1) * pitch + j] - m) * r;
+            const float gg0 = gx.x * lnw_s[c], gg1 = gx.y * lnw_s[c + 1];
+            s1 += gg0 + gg1;
+            s2 = fmaf(gg0, xh0, fmaf(gg1, xh1, s2));
+            aw0[k] = fmaf(gx.x, xh0, aw0[k]); aw1[k] = fmaf(gx.y, xh1, aw1[k]);
+            ab0[k] += gx.x; ab1[k] += gx.y;
+          }
+        }
+        const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+          const int c = 2 * lane + 64 * k;
+          if (c < C) {
+            const float2 gx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&graw[k]));
+            const float xh0 = (tile[c * pitch + j] - m) * r, xh1 = (tile[(c + 1) * pitch + j] - m) * r;
+            tile[c * pitch + j] = r * (gx.x * lnw_s[c] - m1 - xh0 * m2);
+            tile[(c + 1) * pitch + j] = r * (gx.y * lnw_s[c + 1] - m1 - xh1 * m2);
+          }
+        }
+        continue;
+      }
       for (int c = lane; c < C; c += 32) {
         const float gx = bf(gp[c]);
         const float xh = (tile[c * pitch + j] - m) * r;
@@ -331,6 +425,17 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
     }
   }
   __syncthreads();
+  if (regpath) {
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      const int c = 2 * lane + 64 * k;
+      if (c < C) {
+        accw[(warp * 2 + 0) * C + c] = aw0[k]; accw[(warp * 2 + 0) * C + c + 1] = aw1[k];
+        accw[(warp * 2 + 1) * C + c] = ab0[k]; accw[(warp * 2 + 1) * C + c + 1] = ab1[k];
+      }
+    }
+    __syncthreads();
+  }
   float* o = part + (size_t)blockIdx.x * 6 * C;
   for (int c = tid; c < C; c += kThreads) {
     float w0 = 0.f, w1 = 0.f;
@@ -550,13 +655,33 @@ int residual_fwd(const float* x, const void* h2, const float* gamma, const float
 
 int residual_bwd_parts(int N, int C, int HW) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, kWarps, &smem);
+  Geo g = make_geo(N, C, HW, 2 * kWarps, &smem);
   return grid_for(g, smem);
+}
+int gelu_bwd_bias_parts(long long rows, int K) {
+  (void)K;
+  long long ctas = 4LL * sm_count();
+  if (ctas > rows) ctas = rows;
+  return (int)(ctas < 1 ? 1 : ctas);
+}
+int gelu_bwd_bias(const void* da, const void* h, void* dh, float* part, long long rows, int K, cudaStream_t st) {
+  SLAK_REQUIRE(K % 8 == 0 && K > 0, SLAK_ERR_UNSUPPORTED, "hidden width %d must be a multiple of 8", K);
+  const int grid = gelu_bwd_bias_parts(rows, K);
+  const int rows_per_cta = (int)((rows + grid - 1) / grid);
+  const int nv = K / 8;
+  const int rsubs = nv >= kThreads ? 1 : kThreads / nv;
+  const size_t smem = (size_t)rsubs * K * sizeof(float);
+  SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "hidden width %d too large", K);
+  SLAK_CUDA_TRY(cudaFuncSetAttribute(gelu_bwd_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gelu_bwd_bias_kernel<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh,
+                                                    part, rows, K, rows_per_cta);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
 }
 int residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2, float* dgamma_part,
                  int N, int C, int HW, cudaStream_t st) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, kWarps, &smem);
+  Geo g = make_geo(N, C, HW, 2 * kWarps, &smem);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
   const int vp = pick_vp(HW, dout, dout, dout, dout);
   const int grid = grid_for(g, smem);
@@ -571,14 +696,14 @@ int residual_bwd(const float* dout, const void* h2, const float* gamma, const fl
 
 int bn3_sum_ln_bwd_parts(int N, int C, int HW) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, kWarps * 2 + 4, &smem);
+  Geo g = make_geo(N, C, HW, kWarps * 2 + 5, &smem);
   return grid_for(g, smem);
 }
 int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
                    const float* shift, const float* lnw, const float* mu, const float* rstd, void* du, float* part,
                    int N, int C, int HW, cudaStream_t st) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, kWarps * 2 + 4, &smem);
+  Geo g = make_geo(N, C, HW, kWarps * 2 + 5, &smem);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
   const int vp = pick_vp(HW, y1, y2, y3, du);
   const int grid = grid_for(g, smem);

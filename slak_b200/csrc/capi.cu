@@ -28,7 +28,8 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
                int N, int C, int H, int W, int KL, float* stats, cudaStream_t st);
 int lk3_fwd_tc_splits(int N, int C, int H, int W);
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
-               int N, int C, int H, int W, int KL, int KN, int flip, cudaStream_t st);
+               const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
+               cudaStream_t st);
 size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL);
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
@@ -51,6 +52,8 @@ int residual_fwd(const float* x, const void* h2, const float* gamma, const float
 int residual_bwd_parts(int N, int C, int HW);
 int residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2, float* dgamma_part,
                  int N, int C, int HW, cudaStream_t st);
+int gelu_bwd_bias_parts(long long rows, int K);
+int gelu_bwd_bias(const void* da, const void* h, void* dh, float* part, long long rows, int K, cudaStream_t st);
 int bn3_sum_ln_bwd_parts(int N, int C, int HW);
 int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
                    const float* shift, const float* lnw, const float* mu, const float* rstd, void* du, float* part,
@@ -166,9 +169,23 @@ SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const v
   SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, dtype), SLAK_ERR_UNSUPPORTED,
                "fused bwd_data covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
   cudaStream_t st = (cudaStream_t)stream;
-  rc = tc::lk_conv_tc(nullptr, nullptr, dy3, w3, nullptr, tmp, N, C, H, W, KL, KS, /*flip=*/1, st);
+  rc = tc::lk_conv_tc(nullptr, nullptr, dy3, w3, nullptr, tmp, nullptr, nullptr, N, C, H, W, KL, KS, /*flip=*/1, st);
   if (rc) return rc;
-  return tc::lk_conv_tc(dy1, w1, dy2, w2, tmp, dx, N, C, H, W, KL, KL, /*flip=*/1, st);
+  return tc::lk_conv_tc(dy1, w1, dy2, w2, tmp, dx, nullptr, nullptr, N, C, H, W, KL, KL, /*flip=*/1, st);
+}
+
+SLAK_API int slak_lk_branches_bwd_data_f32(const void* dy1, const void* dy2, const void* dy3, const float* w1,
+                                           const float* w2, const float* w3, const float* addend, float* dx,
+                                           void* tmp, int N, int C, int H, int W, int KL, int KS, void* stream) {
+  int rc = check_conv_args(dy1, w1, dx, N, C, H, W, KL, KS, SLAK_BF16, SLAK_F32);
+  if (rc) return rc;
+  SLAK_REQUIRE(dy2 && dy3 && w2 && w3 && tmp, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, SLAK_BF16), SLAK_ERR_UNSUPPORTED,
+               "fused bwd_data covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = tc::lk_conv_tc(nullptr, nullptr, dy3, w3, nullptr, tmp, nullptr, nullptr, N, C, H, W, KL, KS, /*flip=*/1, st);
+  if (rc) return rc;
+  return tc::lk_conv_tc(dy1, w1, dy2, w2, tmp, nullptr, addend, dx, N, C, H, W, KL, KL, /*flip=*/1, st);
 }
 
 SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS) {
@@ -248,6 +265,13 @@ SLAK_API int slak_block_residual_bwd(const float* dout, const void* h2, const fl
                                      float* dgamma_part, int N, int C, int HW, void* stream) {
   SLAK_REQUIRE(dout && h2 && gamma && dh2 && dgamma_part && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
   return blk::residual_bwd(dout, h2, gamma, dp, dh2, dgamma_part, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_gelu_bwd_bias_parts(int64_t rows, int K) { return blk::gelu_bwd_bias_parts(rows, K); }
+
+SLAK_API int slak_gelu_bwd_bias(const void* da, const void* h, void* dh, float* part, int64_t rows, int K, void* stream) {
+  SLAK_REQUIRE(da && h && dh && part && rows > 0 && K > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::gelu_bwd_bias(da, h, dh, part, rows, K, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_bn3_sum_ln_bwd_parts(int N, int C, int HW) { return blk::bn3_sum_ln_bwd_parts(N, C, HW); }

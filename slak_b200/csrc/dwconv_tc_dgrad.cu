@@ -51,7 +51,9 @@ struct DgradParams {
   const float* wt;                 // [C][KL][5] taps of the transposed (vertical-long) path, or nullptr
   const float* wn;                 // [C][5][KN] taps of the natural path
   const __nv_bfloat16* addend;     // [N,C,H,W] or nullptr
-  __nv_bfloat16* out;
+  const float* addend_f32;         // [N,C,H,W] fp32 or nullptr (e.g. the shortcut gradient of a Block)
+  __nv_bfloat16* out;              // bf16 result, or nullptr when out_f32 is given
+  float* out_f32;
   int N, C, H, W, KL, KN, flip, has_t, splits, units_per_c;
 };
 
@@ -326,7 +328,12 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int j = 0; j < T / E; ++j)
           if (j < PR) {
             if (P.addend) add_bf16_piece<E>(v + j * E, P.addend + rbase + j * E);
-            store_bf16_piece<E>(P.out + rbase + j * E, v + j * E);
+            if (P.out_f32) {
+              if (P.addend_f32) add_f32_piece<E>(v + j * E, P.addend_f32 + rbase + j * E);
+              store_f32_piece<E>(P.out_f32 + rbase + j * E, v + j * E);
+            } else {
+              store_bf16_piece<E>(P.out + rbase + j * E, v + j * E);
+            }
           }
       }
     }
@@ -351,7 +358,8 @@ static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParam
 
 // out = conv(in_t, wt [C,KL,5]) + conv(in_n, wn [C,5,KN]) + addend ; in_t/wt may be null together
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
-               int N, int C, int H, int W, int KL, int KN, int flip, cudaStream_t st) {
+               const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
+               cudaStream_t st) {
   const TcShape s = tc_shape(H, W);
   SLAK_REQUIRE(s.tile != 0, SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   CUtensorMap mt, mn;
@@ -364,6 +372,7 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
   DgradParams P;
   P.in_t = (const __nv_bfloat16*)in_t; P.in_n = (const __nv_bfloat16*)in_n;
   P.wt = wt; P.wn = wn; P.addend = (const __nv_bfloat16*)addend; P.out = (__nv_bfloat16*)out;
+  P.addend_f32 = addend_f32; P.out_f32 = out_f32;
   P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL; P.KN = KN; P.flip = flip; P.has_t = in_t ? 1 : 0;
   if (s.tile == 64) return launch_dgrad<64, 16, true>(mt, mn, P, st);
   if (s.tile == 32) {

@@ -182,6 +182,36 @@ __device__ __forceinline__ void add_bf16_piece(uint32_t* v, const __nv_bfloat16*
     v[0] = __float_as_uint(__uint_as_float(v[0]) + __bfloat162float(*src));
   }
 }
+// fp32 variants: E floats added from / stored to global
+template <int E>
+__device__ __forceinline__ void add_f32_piece(uint32_t* v, const float* src) {
+  if constexpr (E >= 4) {
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(src + k);
+      v[k] = __float_as_uint(__uint_as_float(v[k]) + t.x); v[k + 1] = __float_as_uint(__uint_as_float(v[k + 1]) + t.y);
+      v[k + 2] = __float_as_uint(__uint_as_float(v[k + 2]) + t.z); v[k + 3] = __float_as_uint(__uint_as_float(v[k + 3]) + t.w);
+    }
+  } else if constexpr (E == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(src);
+    v[0] = __float_as_uint(__uint_as_float(v[0]) + t.x); v[1] = __float_as_uint(__uint_as_float(v[1]) + t.y);
+  } else {
+    v[0] = __float_as_uint(__uint_as_float(v[0]) + src[0]);
+  }
+}
+template <int E>
+__device__ __forceinline__ void store_f32_piece(float* dst, const uint32_t* v) {
+  if constexpr (E >= 4) {
+#pragma unroll
+    for (int k = 0; k < E; k += 4)
+      *reinterpret_cast<float4*>(dst + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]),
+                                                        __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+  } else if constexpr (E == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  } else {
+    dst[0] = __uint_as_float(v[0]);
+  }
+}
 template <int E>
 __device__ __forceinline__ void copy_piece(__nv_bfloat16* dst, const uint8_t* src) {
   if constexpr (E == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
