@@ -63,8 +63,15 @@ class FusedBlockFunction(torch.autograd.Function):
             sums = torch.empty((C, 6), dtype=torch.float64, device=dev)
             need = lib.slak_block_conv_fwd_workspace(N, C, H, W)
             ws = ops._workspace(need, dev)
+            timed = ops._profiled(N, C, H, W, KL, 5, bf16)
+            if timed:
+                ev = (ops._new_event(), ops._new_event())
+                ev[0].record()
             _ck(lib.slak_block_conv_fwd(_p(xb), _p(w1), _p(w2), _p(w3), _p(y1), _p(y2), _p(y3), _p(sums), _p(ws),
                                         ws.numel(), N, C, H, W, KL, st), "slak_block_conv_fwd")
+            if timed:
+                ev[1].record()
+                ops._prof["events"].append(ev)
             count = float(N * HW)
             dist, world = _dist_world() if sync else (None, 1)
             if world > 1:                     # SyncBatchNorm: statistics over the global batch

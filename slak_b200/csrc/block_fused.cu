@@ -402,11 +402,15 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
     }
     __syncthreads();
     // phase 3: write du (NCHW bf16) and accumulate the BatchNorm reductions; one warp per channel
-    for (int c = warp; c < C; c += kWarps) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int jv = lane; jv < vec_per_row; jv += 32) {
+    if (vec_per_row <= 32) {
+      // vec_per_row (a power of two) consecutive lanes share a channel: segmented shuffle reduction
+      const int total = C * vec_per_row;
+      for (int idx0 = 0; idx0 < total; idx0 += kThreads) {
+        const int idx = idx0 + tid;
+        const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
         const int j = jv * VP;
-        if (j < npix) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (idx < total && j < npix) {
           const size_t off = ((size_t)n * C + c) * HW + p0 + j;
           float d[VP], q1[VP], q2[VP], q3[VP];
 #pragma unroll
@@ -419,9 +423,34 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
             a0 += dr; a1 = fmaf(dr, q1[k], a1); a2 = fmaf(dr, q2[k], a2); a3 = fmaf(dr, q3[k], a3);
           }
         }
+        for (int o = vec_per_row >> 1; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+        }
+        if (idx < total && jv == 0) { accs[c] += a0; accs[C + c] += a1; accs[2 * C + c] += a2; accs[3 * C + c] += a3; }
       }
-      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
-      if (lane == 0) { accs[c] += a0; accs[C + c] += a1; accs[2 * C + c] += a2; accs[3 * C + c] += a3; }
+    } else {
+      for (int c = warp; c < C; c += kWarps) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int jv = lane; jv < vec_per_row; jv += 32) {
+          const int j = jv * VP;
+          if (j < npix) {
+            const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+            float d[VP], q1[VP], q2[VP], q3[VP];
+#pragma unroll
+            for (int k = 0; k < VP; ++k) d[k] = tile[c * pitch + j + k];
+            st_bf16<VP>(du + off, d);
+            ld_bf16<VP>(y1 + off, q1); ld_bf16<VP>(y2 + off, q2); ld_bf16<VP>(y3 + off, q3);
+#pragma unroll
+            for (int k = 0; k < VP; ++k) {
+              const float dr = __bfloat162float(__float2bfloat16_rn(d[k]));
+              a0 += dr; a1 = fmaf(dr, q1[k], a1); a2 = fmaf(dr, q2[k], a2); a3 = fmaf(dr, q3[k], a3);
+            }
+          }
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+        if (lane == 0) { accs[c] += a0; accs[C + c] += a1; accs[2 * C + c] += a2; accs[3 * C + c] += a3; }
+      }
     }
   }
   __syncthreads();
@@ -555,8 +584,9 @@ __global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, double coun
 static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_bytes) {
   Geo g{};
   g.N = N; g.C = C; g.HW = HW;
-  // tile of PIX pixels x C channels in fp32; PIX a multiple of 8, about 48 KB
-  int pix = (48 * 1024 / 4) / C;
+  // tile of PIX pixels x C channels in fp32; PIX a multiple of 8, about 24 KB (several CTAs per SM: the
+  // phases of these kernels are latency-bound, occupancy is what hides it)
+  int pix = (24 * 1024 / 4) / C;
   pix = pix >= 128 ? 128 : (pix >= 64 ? 64 : (pix >= 32 ? 32 : (pix >= 16 ? 16 : 8)));
   while (pix > 8 && pix / 2 >= HW) pix /= 2;
   g.PIX = pix;
@@ -575,7 +605,7 @@ static int pick_vp(int HW, const void* a, const void* b, const void* c, const vo
 }
 static int grid_for(const Geo& g, size_t smem) {
   int per_sm = smem > 0 ? (int)(200 * 1024 / smem) : 4;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 6) per_sm = 6;
   if (per_sm < 1) per_sm = 1;
   int grid = sm_count() * per_sm;
   if (grid > g.total_tiles) grid = g.total_tiles;
@@ -627,7 +657,7 @@ int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* 
   const int vp = pick_vp(HW, y1, y2, y3, y1);
   const int grid = grid_for(g, smem);
 #define CALL(V)                                                                                                   \
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(bn3_sum_ln_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  SLAK_SET_MAX_SMEM(bn3_sum_ln_fwd_kernel<V>, smem); \
   bn3_sum_ln_fwd_kernel<V><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)y1, (const __nv_bfloat16*)y2,        \
       (const __nv_bfloat16*)y3, scale, shift, lnw, lnb, eps, (__nv_bfloat16*)xn, mu, rstd, g)
   SLAK_VP_DISPATCH(vp, CALL);
@@ -645,7 +675,7 @@ int residual_fwd(const float* x, const void* h2, const float* gamma, const float
   if (vp == 8 && HW % 8 != 0) vp = 1;
   const int grid = grid_for(g, smem);
 #define CALL(V)                                                                                                   \
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(residual_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  SLAK_SET_MAX_SMEM(residual_fwd_kernel<V>, smem); \
   residual_fwd_kernel<V><<<grid, kThreads, smem, st>>>(x, (const __nv_bfloat16*)h2, gamma, dp, out, (__nv_bfloat16*)out_bf16, g)
   SLAK_VP_DISPATCH(vp, CALL);
 #undef CALL
@@ -672,7 +702,7 @@ int gelu_bwd_bias(const void* da, const void* h, void* dh, float* part, long lon
   const int rsubs = nv >= kThreads ? 1 : kThreads / nv;
   const size_t smem = (size_t)rsubs * K * sizeof(float);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "hidden width %d too large", K);
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(gelu_bwd_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SLAK_SET_MAX_SMEM(gelu_bwd_bias_kernel, smem);
   gelu_bwd_bias_kernel<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh,
                                                     part, rows, K, rows_per_cta);
   SLAK_CUDA_TRY(cudaGetLastError());
@@ -686,7 +716,7 @@ int residual_bwd(const float* dout, const void* h2, const float* gamma, const fl
   const int vp = pick_vp(HW, dout, dout, dout, dout);
   const int grid = grid_for(g, smem);
 #define CALL(V)                                                                                                   \
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(residual_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  SLAK_SET_MAX_SMEM(residual_bwd_kernel<V>, smem); \
   residual_bwd_kernel<V><<<grid, kThreads, smem, st>>>(dout, (const __nv_bfloat16*)h2, gamma, dp, (__nv_bfloat16*)dh2, dgamma_part, g)
   SLAK_VP_DISPATCH(vp, CALL);
 #undef CALL
@@ -708,7 +738,7 @@ int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* 
   const int vp = pick_vp(HW, y1, y2, y3, du);
   const int grid = grid_for(g, smem);
 #define CALL(V)                                                                                                   \
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(bn3_sum_ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  SLAK_SET_MAX_SMEM(bn3_sum_ln_bwd_kernel<V>, smem); \
   bn3_sum_ln_bwd_kernel<V><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)dxn, (const __nv_bfloat16*)y1,       \
       (const __nv_bfloat16*)y2, (const __nv_bfloat16*)y3, scale, shift, lnw, mu, rstd, (__nv_bfloat16*)du, part, g)
   SLAK_VP_DISPATCH(vp, CALL);

@@ -22,6 +22,17 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
+// raise a kernel's dynamic shared-memory limit once per call site (not on every launch: the attribute
+// call must not happen while a CUDA graph is being captured more often than needed)
+#define SLAK_SET_MAX_SMEM(kern, bytes)                                                             \
+  do {                                                                                             \
+    static int _slak_cur_smem = 0;                                                                 \
+    if ((int)(bytes) > _slak_cur_smem) {                                                           \
+      SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _slak_cur_smem = (int)(bytes);                                                               \
+    }                                                                                              \
+  } while (0)
+
 #define SLAK_REQUIRE(cond, code, ...)                                              \
   do {                                                                             \
     if (!(cond)) {                                                                 \

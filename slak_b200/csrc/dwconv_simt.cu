@@ -571,7 +571,7 @@ static int launch_fwd_fast(const void* x, const void* w, void* y, int N, int C, 
                            int flip, cudaStream_t st) {
   auto kern = dw_fwd_fast_kernel<T, WT, KS, VERT>;
   size_t smem = (size_t)(g.wfloats + g.G * g.rows * g.pitch + g.G * g.H * g.opitch) * 4;
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SLAK_SET_MAX_SMEM(kern, smem);
   // CTAs: C x parts, ~4 waves of 2 CTAs/SM, each CTA at least 2 iterations when the batch allows
   int target = 4 * 2 * sm_count();
   int parts = (target + C - 1) / C;
@@ -608,7 +608,7 @@ static int launch_fwd_generic(const void* x, const void* w, void* y, int N, int 
   const int th = GT + kh - 1, tw = GT + kw - 1;
   size_t smem = (size_t)(((kh * kw + 3) & ~3) + th * (tw | 1)) * 4;
   SLAK_REQUIRE(smem <= 220 * 1024, SLAK_ERR_UNSUPPORTED, "kernel %dx%d too large for the generic path", kh, kw);
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SLAK_SET_MAX_SMEM(kern, smem);
   int target = 8 * sm_count();
   int parts = (target + C - 1) / C;
   if (parts > N) parts = N;
@@ -686,7 +686,7 @@ static int launch_wgrad_fast(const void* x, const void* dy, float* partial, int 
   auto kern = dw_wgrad_fast_kernel<T, KS, VERT>;
   const FastGeom& g = p.g;
   size_t smem = (size_t)(2 * g.G * g.rows * g.pitch + NWARPS * RB * KS) * 4;
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SLAK_SET_MAX_SMEM(kern, smem);
   dim3 grid(C, p.parts, g.zchunks);
   kern<<<grid, NTHREADS, smem, st>>>((const T*)x, (const T*)dy, partial, N, C, g, p.n_per_cta);
   SLAK_CUDA_TRY(cudaGetLastError());
@@ -712,7 +712,7 @@ static int wgrad_typed(const void* dy, const void* x, float* dw, int N, int C, i
     const int th = GT + kh - 1, tw = GT + kw - 1;
     size_t smem = (size_t)(th * (tw | 1) + GT * GT) * 4;
     SLAK_REQUIRE(smem <= 220 * 1024, SLAK_ERR_UNSUPPORTED, "kernel %dx%d too large for the generic path", kh, kw);
-    SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SLAK_SET_MAX_SMEM(kern, smem);
     dim3 grid(C, p.parts, (taps + NTHREADS - 1) / NTHREADS);
     kern<<<grid, NTHREADS, smem, st>>>((const T*)x, (const T*)dy, partial, N, C, H, W, kh, kw, p.n_per_cta);
     SLAK_CUDA_TRY(cudaGetLastError());

@@ -350,7 +350,7 @@ static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParam
   P.units_per_c = (P.N + Cf::PPU - 1) / Cf::PPU;
   P.splits = tc_pick_splits(P.C, P.units_per_c);
   auto kern = lk_dgrad_tc_kernel<T, CB, TMA>;
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::kSmem));
+  SLAK_SET_MAX_SMEM(kern, Cf::kSmem);
   kern<<<P.C * P.splits, dg::kThreads, Cf::kSmem, st>>>(mt, mn, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;

@@ -444,7 +444,7 @@ static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
   P.units_per_c = (P.N + Cfg::PLANES - 1) / Cfg::PLANES;
   P.splits = tc_pick_splits(P.C, P.units_per_c);
   auto kern = lk3_fwd_tc_kernel<T, CB, TMA>;
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  SLAK_SET_MAX_SMEM(kern, Cfg::kSmem);
   kern<<<P.C * P.splits, kThreads, Cfg::kSmem, st>>>(map, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;

@@ -353,7 +353,7 @@ size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL) {
 template <int T, int CB, bool TMA>
 static int launch_wgrad(const CUtensorMap* maps, WgradParams& P, cudaStream_t st) {
   auto kern = lk3_wgrad_tc_kernel<T, CB, TMA>;
-  SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
+  SLAK_SET_MAX_SMEM(kern, wg::kSmemBytes);
   kern<<<P.C * P.splits, wg::kThreads, wg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;

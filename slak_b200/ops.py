@@ -50,6 +50,13 @@ def profile_reset(match) -> None:
     _prof["events"] = []
 
 
+def _new_event():
+    m = _prof["match"]
+    if m is not None and m.get("external_events"):
+        return torch.cuda.Event(enable_timing=True, external=True)    # usable inside CUDA-graph capture
+    return torch.cuda.Event(enable_timing=True)
+
+
 def profile_collect():
     torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for a, b in _prof["events"])
@@ -192,7 +199,7 @@ def lk_branches_forward(x, w1, w2, w3=None):
     timed = tc and _profiled(N, C, H, W, KL, KS, x.dtype)
     with torch.cuda.device(x.device):
         if timed:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev = (_new_event(), _new_event())
             ev[0].record()
         rc = lib.slak_lk_branches_fwd(x.data_ptr(), w1.data_ptr(), w2.data_ptr(),
                                       w3.data_ptr() if w3 is not None else None,

@@ -217,8 +217,14 @@ class Block(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
-        if FUSED_BLOCK and block_mod.fused_block_supported(self, x):
-            return block_mod.fused_block_forward(self, x)       # one autograd node, see slak_b200/block.py
+        if FUSED_BLOCK and x.is_cuda and torch.is_autocast_enabled():
+            # the fused node keeps the residual stream in fp32 and NCHW-contiguous; the first Block of a stage
+            # receives the (possibly bf16 / channels_last) output of the downsampling conv: bf16 -> fp32 is exact
+            # and the reference's `input + gamma*x` promotes to fp32 there anyway (models/SLaK.py:161-165)
+            xf = x if x.dtype == torch.float32 else x.float()
+            xf = xf.contiguous()
+            if block_mod.fused_block_supported(self, xf):
+                return block_mod.fused_block_forward(self, xf)   # one autograd node, see slak_b200/block.py
         shortcut = x
         if x.is_cuda and torch.is_autocast_enabled():
             # the depthwise branch is autocast-eligible here (the reference pins fp32 inputs to its
