@@ -5,20 +5,26 @@
 //
 // Formulation (banded-Toeplitz GEMMs, per channel):
 //   long axis of a branch  -> contraction (K) against a Toeplitz matrix of the taps, built in
-//                             shared memory once per CTA (B operand, K-major, SWIZZLE_128B)
+//                             shared memory per channel (B operand, K-major, SWIZZLE_128B)
 //   short axis (5 taps)    -> five accumulating MMAs whose A operand (the image planes) starts
 //                             (t-2) ROWS later: a row shift is a +128-byte descriptor offset
 //   y2|y3 [(plane,p), q]  += X [(plane,p+r-2), w]   * [T2_r ; T3_r][q, w]    M=128 N=2T K=T
 //   y1^T  [(plane,q), p]  += X^T[(plane,q+s-2), h]  * T1_s[p, h]             M=128 N=T  K=T
-//   A plane occupies a T x T tile (T = 64, 32 or 16 >= H+2, W+2) that is zero beyond H x W; M=128
-//   stacks 128/T planes of the same channel and the zero rows double as the "same" padding
-//   between stacked planes.
+//   A plane occupies a T x T block (T = 64, 32 or 16 >= H+2, W+2) that is zero beyond H x W.  A unit is one
+//   128-row x 64-column SWIZZLE_128B tile: 128/T row groups x 64/T column bands = 2 / 8 / 32 planes
+//   of one channel (~12.5 KB of input whatever the class); the zero rows double as the "same"
+//   padding between stacked planes.
 //   X is staged by TMA (T=64, W%8==0: 3-D tiled map, OOB zero fill) or by cp.async pieces; X^T is
 //   made in shared memory with ldmatrix.trans/stmatrix.
 //
-// Warp roles (320 threads): w0 loader | w1 MMA issuer | w2-3 transposers (w2 owns TMEM alloc) |
+// A CTA walks a contiguous range of (channel, unit) work items.  For T=64 a range stays inside one
+// channel (one Toeplitz set, 120 KB); for the small classes the CTAs are persistent over many
+// channels and a builder warp prepares the next channel's Toeplitz set (double-buffered) while the
+// pipeline runs, so short channels do not pay a pipeline drain.
+//
+// Warp roles (352 threads): w0 loader | w1 MMA issuer | w2-3 transposers (w2 owns TMEM alloc) |
 // w4-7 epilogue (TMEM -> registers -> bf16 -> global; y1 is transposed back through smem) |
-// w8-9 extra loaders (cp.async path only).
+// w8-9 extra loaders (cp.async path only) | w10 Toeplitz builder.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
@@ -32,22 +38,23 @@ constexpr int kUnitBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kPad = 1024;                       // zero rows before/after a unit tile
 constexpr int kXSlot = kPad + kUnitBytes + kPad; // 18 KB
 constexpr int kNumTransposerWarps = 2;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;
 
 template <int T> struct FwdCfg {
-  static constexpr int PPU = 128 / T;            // planes per unit
+  static constexpr int PPU = 128 / T;            // row groups per unit
   static constexpr int KSTEPS = T / 16;
-  static constexpr int UPS = 64 / T;             // 128-row groups per unit: group b fills the T-element band b of the rows
-  static constexpr int PLANES = PPU * UPS;       // planes per unit (2, 8, 32): ~12.5 KB of input for every tile class
-  static constexpr int NSTAGE = kStages;         // X units in flight
+  static constexpr int UPS = 64 / T;             // column bands per unit
+  static constexpr int PLANES = PPU * UPS;       // planes per unit (2, 8, 32)
+  static constexpr int NT = (T == 64) ? 1 : 2;   // Toeplitz sets (double-buffered for the multi-channel classes)
   static constexpr int kToep1 = 5 * T * 128;
   static constexpr int kToep23 = 5 * 2 * T * 128;
-  static constexpr int kOffToep1 = 0;
-  static constexpr int kOffToep23 = kToep1;
-  static constexpr int kOffXN = kOffToep23 + kToep23;
+  static constexpr int kToepSet = kToep1 + kToep23;
+  static constexpr int kOffToep = 0;
+  static constexpr int kOffXN = kOffToep + NT * kToepSet;
   static constexpr int kOffXT = kOffXN + kStages * kXSlot;
   static constexpr int kOffY1 = kOffXT + kXSlot;
-  static constexpr int kOffBar = kOffY1 + kUnitBytes;
+  static constexpr int kOffW = kOffY1 + kUnitBytes;          // fp32 tap staging of the builder warp (4 KB)
+  static constexpr int kOffBar = kOffW + 4096;
   static constexpr int kSmem = kOffBar + 1024 + 1024;
   static constexpr int kAccCols = 3 * T * UPS;   // 192 for every class
   static constexpr int kTmemCols = 512;
@@ -58,16 +65,58 @@ struct FwdParams {
   const float* w1; const float* w2; const float* w3;       // fp32 taps [C,KL,5] [C,5,KL] [C,5,5]
   __nv_bfloat16* y1; __nv_bfloat16* y2; __nv_bfloat16* y3;
   int N, C, H, W, KL;
-  int splits;            // CTAs per channel
   int units_per_c;       // ceil(N / PLANES)
-  float* stats;          // optional [C][splits][6]: per-CTA (sum, sum of squares) of y1, y2, y3 (as rounded to bf16)
+  int per_cta;           // work items per CTA; items are (channel, unit) in channel-major order.  For T=64
+                         // per_cta divides the channel into `splits` ranges (grid = C * splits)
+  int splits;            // T=64: CTAs per channel; small classes: stats slots per channel
+  float* stats;          // optional [C][splits][6]: per-CTA (sum, sum of squares) of y1, y2, y3 (fp32, before rounding)
 };
+
+// Banded Toeplitz operands of one channel (K-major SWIZZLE_128B): five T1_s tiles at tp, then five [T2_r ; T3_r] tiles.
+template <int T>
+__device__ __forceinline__ void build_toeplitz(uint8_t* tp, const float* w1s, const float* w2s, const float* w3s,
+                                               int KL, int pad, int t0, int nthr) {
+  using Cfg = FwdCfg<T>;
+  constexpr int CH = T / 8;                                  // 16-byte chunks per row that are ever read
+  // T1_s[p][h] = w1[h-p+pad][s]
+  for (int ch = t0; ch < 5 * T * CH; ch += nthr) {
+    const int s = ch / (T * CH), rem = ch - s * (T * CH), p = rem / CH, k8 = rem - p * CH;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t = (k8 * 8 + j) - p + pad;
+      v[j] = (t >= 0 && t < KL) ? w1s[t * 5 + s] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(tp + s * (T * 128) + p * 128 + ((k8 ^ (p & 7)) << 4)) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  // T23_r rows 0..T-1: T2_r[q][w] = w2[r][w-q+pad] ; rows T..2T-1: T3_r[q][w] = w3[r][w-q+2]
+  for (int ch = t0; ch < 5 * 2 * T * CH; ch += nthr) {
+    const int r = ch / (2 * T * CH), rem = ch - r * (2 * T * CH), row = rem / CH, k8 = rem - row * CH;
+    float v[8];
+    if (row < T) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = (k8 * 8 + j) - row + pad;
+        v[j] = (t >= 0 && t < KL) ? w2s[r * KL + t] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = (k8 * 8 + j) - (row - T) + 2;
+        v[j] = (t >= 0 && t < 5) ? w3s[r * 5 + t] : 0.f;
+      }
+    }
+    *reinterpret_cast<uint4*>(tp + Cfg::kToep1 + r * (2 * T * 128) + row * 128 + ((k8 ^ (row & 7)) << 4)) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
 
 template <int T, int CB, bool TMA>
 __global__ void __launch_bounds__(kThreads, 1)
 lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   using Cfg = FwdCfg<T>;
-  constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2, UPS = Cfg::UPS, NSTAGE = Cfg::NSTAGE;
+  constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2, UPS = Cfg::UPS, PLANES = Cfg::PLANES, NT = Cfg::NT;
   constexpr int kNumLoaders = TMA ? 1 : 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -75,24 +124,37 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   uint8_t* sm = smem_raw + (base - raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c = blockIdx.x / P.splits;
-  const int split = blockIdx.x % P.splits;
-  const int u_begin = (int)(((long long)P.units_per_c * split) / P.splits);
-  const int u_end = (int)(((long long)P.units_per_c * (split + 1)) / P.splits);
-  const int n_units = u_end - u_begin;
+  const int upc = P.units_per_c;
+  // work range of this CTA: global item g = c * upc + u
+  long long g0, g1;
+  int slot0;                                  // stats slot of this CTA inside its first channel
+  if (T == 64) {
+    const int c = blockIdx.x / P.splits, split = blockIdx.x % P.splits;
+    g0 = (long long)c * upc + ((long long)upc * split) / P.splits;
+    g1 = (long long)c * upc + ((long long)upc * (split + 1)) / P.splits;
+    slot0 = split;
+  } else {
+    const long long total = (long long)P.C * upc;
+    g0 = (long long)blockIdx.x * P.per_cta;
+    g1 = g0 + P.per_cta < total ? g0 + P.per_cta : total;
+    if (g0 > total) g0 = total;
+    slot0 = 0;
+  }
+  const int n_units = (int)(g1 - g0);
+  const int c_first = n_units > 0 ? (int)(g0 / upc) : 0;
+  const int c_last = n_units > 0 ? (int)((g1 - 1) / upc) : -1;
   const int KL = P.KL, pad = KL / 2, H = P.H, W = P.W;
 
-  constexpr int PLANES = Cfg::PLANES;
-  constexpr int B_XN_FULL = 0, B_XN_EMPTY = NSTAGE, B_XT_FULL = 2 * NSTAGE, B_XT_EMPTY = B_XT_FULL + 1,
-                B_ACC_FULL = B_XT_EMPTY + 1, B_ACC_EMPTY = B_ACC_FULL + kAccBufs;
+  constexpr int B_XN_FULL = 0, B_XN_EMPTY = kStages, B_XT_FULL = 2 * kStages, B_XT_EMPTY = B_XT_FULL + 1,
+                B_ACC_FULL = B_XT_EMPTY + 1, B_ACC_EMPTY = B_ACC_FULL + kAccBufs, B_TP_FULL = B_ACC_EMPTY + kAccBufs,
+                B_TP_EMPTY = B_TP_FULL + NT;
   const uint32_t bar0 = base + Cfg::kOffBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cfg::kOffBar + 768);
-  // a unit = one 128-row x 64-column slot: row group pl (T rows) x column band b (T columns) holds plane b*PPU + pl
   auto XN_ADDR = [&](int s) { return base + Cfg::kOffXN + s * kXSlot + kPad; };
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(BAR(B_XN_FULL + s), 1);                          // TMA expect_tx arrive / loader lane 0
       mbar_init(BAR(B_XN_EMPTY + s), 1 + kNumTransposerWarps);   // MMA commit + transposers done reading
     }
@@ -102,75 +164,48 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       mbar_init(BAR(B_ACC_FULL + a), 1);                         // MMA commit
       mbar_init(BAR(B_ACC_EMPTY + a), 4);                        // one arrival per epilogue warp
     }
+    for (int s = 0; s < NT; ++s) {
+      mbar_init(BAR(B_TP_FULL + s), 1);                          // builder warp
+      mbar_init(BAR(B_TP_EMPTY + s), 1);                         // MMA commit after the channel's last MMA
+    }
     mbar_fence_init();
     if (TMA) tma_prefetch_desc(&xmap);
   }
-
-  // ---- zero the X / X^T slots (pads + tile padding stay zero forever) and build the Toeplitz operands ----
-  {
+  {  // X / X^T slots start as zeros: pads and tile padding are never written afterwards
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < (kStages + 1) * kXSlot / 16; i += kThreads)
       reinterpret_cast<uint4*>(sm + Cfg::kOffXN)[i] = z;
-    float* wst = reinterpret_cast<float*>(sm + Cfg::kOffY1);
-    float* w1s = wst;                 // [KL][5]
-    float* w2s = wst + KL * 5;        // [5][KL]
-    float* w3s = wst + 2 * KL * 5;    // [5][5]
-    for (int i = tid; i < KL * 5; i += kThreads) {
-      w1s[i] = P.w1[(size_t)c * KL * 5 + i];
-      w2s[i] = P.w2[(size_t)c * KL * 5 + i];
-    }
-    if (tid < 25) w3s[tid] = P.w3[(size_t)c * 25 + tid];
-    __syncthreads();
-    constexpr int CH = T / 8;         // 16-byte chunks per row that are ever read
-    // T1_s[p][h] = w1[h-p+pad][s]
-    for (int ch = tid; ch < 5 * T * CH; ch += kThreads) {
-      const int s = ch / (T * CH), rem = ch - s * (T * CH), p = rem / CH, k8 = rem - p * CH;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int t = (k8 * 8 + j) - p + pad;
-        v[j] = (t >= 0 && t < KL) ? w1s[t * 5 + s] : 0.f;
-      }
-      *reinterpret_cast<uint4*>(sm + Cfg::kOffToep1 + s * (T * 128) + p * 128 + ((k8 ^ (p & 7)) << 4)) =
-          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    }
-    // T23_r rows 0..T-1: T2_r[q][w] = w2[r][w-q+pad] ; rows T..2T-1: T3_r[q][w] = w3[r][w-q+2]
-    for (int ch = tid; ch < 5 * 2 * T * CH; ch += kThreads) {
-      const int r = ch / (2 * T * CH), rem = ch - r * (2 * T * CH), row = rem / CH, k8 = rem - row * CH;
-      float v[8];
-      if (row < T) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int t = (k8 * 8 + j) - row + pad;
-          v[j] = (t >= 0 && t < KL) ? w2s[r * KL + t] : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int t = (k8 * 8 + j) - (row - T) + 2;
-          v[j] = (t >= 0 && t < 5) ? w3s[r * 5 + t] : 0.f;
-        }
-      }
-      *reinterpret_cast<uint4*>(sm + Cfg::kOffToep23 + r * (2 * T * 128) + row * 128 + ((k8 ^ (row & 7)) << 4)) =
-          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    }
   }
-  fence_proxy_async();      // generic-proxy writes above are read by the tensor core (async proxy)
+  if (NT == 1 && n_units > 0) {   // single-channel range: every thread helps building the one Toeplitz set
+    float* w1s = reinterpret_cast<float*>(sm + Cfg::kOffW);
+    float* w2s = w1s + KL * 5;
+    float* w3s = w2s + KL * 5;
+    for (int i = tid; i < KL * 5; i += kThreads) {
+      w1s[i] = P.w1[(size_t)c_first * KL * 5 + i];
+      w2s[i] = P.w2[(size_t)c_first * KL * 5 + i];
+    }
+    if (tid < 25) w3s[tid] = P.w3[(size_t)c_first * 25 + tid];
+    __syncthreads();
+    build_toeplitz<T>(sm + Cfg::kOffToep, w1s, w2s, w3s, KL, pad, tid, kThreads);
+  }
+  fence_proxy_async();
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const bool is_loader = (warp == 0) || (!TMA && warp >= 8);
+  const bool is_loader = (warp == 0) || (!TMA && (warp == 8 || warp == 9));
   if (is_loader) {
     if constexpr (TMA) {
       // ================= TMA producer (T = 64: two planes per unit) =================
       if (elect_one()) {
         for (int i = 0; i < n_units; ++i) {
-          const int st = i % NSTAGE, ph = (i / NSTAGE) & 1;
+          const long long g = g0 + i;
+          const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
+          const int st = i % kStages, ph = (i / kStages) & 1;
           mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
-          const int n0 = PLANES * (u_begin + i);
+          const int n0 = PLANES * u;
           const uint32_t dst = XN_ADDR(st);
           mbar_expect_tx(BAR(B_XN_FULL + st), kUnitBytes);
 #pragma unroll
@@ -185,14 +220,35 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
       for (int i = lj; i < n_units; i += kNumLoaders) {
-        const int s = lj, ph = (i / NSTAGE) & 1;              // lj == i % NSTAGE
+        const long long g = g0 + i;
+        const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
+        const int s = lj, ph = (i / kStages) & 1;             // lj == i % kStages
         mbar_wait(BAR(B_XN_EMPTY + s), ph ^ 1);
         const uint32_t tile = XN_ADDR(s);
-        const int n0 = PLANES * (u_begin + i);
-        for (int q = 0; q < PLANES; ++q)
-          if (n0 + q < P.N)
-            load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.x) + ((size_t)(n0 + q) * P.C + c) * plane_bytes,
-                                 tile, (q % PPU) * T, (q / PPU) * (T / 8), lane);
+        const int n0 = PLANES * u;
+        if (CB == 2 && pm.count >= 0 && pm.count <= 2) {
+          // batches of 8 planes: loads first, then stores
+          for (int q0 = 0; q0 < PLANES; q0 += 8) {
+            const uint8_t* srcs[8]; int r0s[8], c0s[8];
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int q = q0 + j;
+              srcs[j] = reinterpret_cast<const uint8_t*>(P.x); r0s[j] = 0; c0s[j] = 0;
+              if (q < PLANES && n0 + q < P.N) {
+                srcs[j] = reinterpret_cast<const uint8_t*>(P.x) + ((size_t)(n0 + q) * P.C + c) * plane_bytes;
+                r0s[j] = (q % PPU) * T; c0s[j] = (q / PPU) * (T / 8);
+                cnt = j + 1;
+              }
+            }
+            if constexpr (CB == 2) load_plane_blocks_cb2<8>(pm, srcs, tile, r0s, c0s, cnt, lane);
+          }
+        } else {
+          for (int q = 0; q < PLANES; ++q)
+            if (n0 + q < P.N)
+              load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.x) + ((size_t)(n0 + q) * P.C + c) * plane_bytes,
+                                   tile, (q % PPU) * T, (q / PPU) * (T / 8), lane);
+        }
         cp_async_commit();
         cp_async_wait_all();
         fence_proxy_async();
@@ -205,8 +261,16 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     if (elect_one()) {
       constexpr uint32_t idesc23 = umma_idesc_bf16(128, 2 * T);
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, T);
+      int cur_c = -1, k = -1;                         // k = index of the current channel inside this CTA's range
       for (int i = 0; i < n_units; ++i) {
-        const int st = i % NSTAGE, ph = (i / NSTAGE) & 1;
+        const int c = (int)((g0 + i) / upc);
+        if (c != cur_c) {
+          if (k >= 0) umma_commit(BAR(B_TP_EMPTY + (k % NT)));   // previous channel's Toeplitz set is free once its MMAs retire
+          cur_c = c; ++k;
+          if (NT > 1) mbar_wait(BAR(B_TP_FULL + (k % NT)), (k / NT) & 1);
+        }
+        const uint32_t toep = base + Cfg::kOffToep + (k % NT) * Cfg::kToepSet;
+        const int st = i % kStages, ph = (i / kStages) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
         mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);   // epilogue drained this accumulator buffer
         mbar_wait(BAR(B_XN_FULL + st), ph);          // X landed
@@ -215,14 +279,14 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         const uint32_t xt = base + Cfg::kOffXT + kPad;
         const uint32_t acc = tmem + ab * Cfg::kAccCols;
 #pragma unroll
-        for (int g = 0; g < UPS; ++g)                // column band g = row-group set g
+        for (int g = 0; g < UPS; ++g)                // column band g
 #pragma unroll
           for (int r = 0; r < 5; ++r)
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              const uint32_t a = xn + (r - 2) * 128 + g * (T * 2) + k * 32;
-              const uint32_t b = base + Cfg::kOffToep23 + r * (2 * T * 128) + k * 32;
-              umma_bf16(acc + g * 3 * T + T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc23, (r | k) != 0);
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint32_t a = xn + (r - 2) * 128 + g * (T * 2) + kk * 32;
+              const uint32_t b = toep + Cfg::kToep1 + r * (2 * T * 128) + kk * 32;
+              umma_bf16(acc + g * 3 * T + T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc23, (r | kk) != 0);
             }
         umma_commit(BAR(B_XN_EMPTY + st));           // X slot free (with the transposers' arrivals)
         mbar_wait(BAR(B_XT_FULL), i & 1);            // X^T written
@@ -232,10 +296,10 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
 #pragma unroll
           for (int s = 0; s < 5; ++s)
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              const uint32_t a = xt + (s - 2) * 128 + g * (T * 2) + k * 32;
-              const uint32_t b = base + Cfg::kOffToep1 + s * (T * 128) + k * 32;
-              umma_bf16(acc + g * 3 * T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc1, (s | k) != 0);
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint32_t a = xt + (s - 2) * 128 + g * (T * 2) + kk * 32;
+              const uint32_t b = toep + s * (T * 128) + kk * 32;
+              umma_bf16(acc + g * 3 * T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc1, (s | kk) != 0);
             }
         umma_commit(BAR(B_XT_EMPTY));                // X^T slot free
         umma_commit(BAR(B_ACC_FULL + ab));           // accumulators ready
@@ -247,7 +311,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     const int m = lane >> 3, kk = lane & 7;     // matrix id within the x4, row within the 8x8 block
     constexpr int NB = T / 8;                   // blocks per plane edge
     for (int i = 0; i < n_units; ++i) {
-      const int st = i % NSTAGE, ph = (i / NSTAGE) & 1;
+      const int st = i % kStages, ph = (i / kStages) & 1;
       mbar_wait(BAR(B_XN_FULL + st), ph);       // X landed
       mbar_wait(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed
       const uint32_t xn = XN_ADDR(st);
@@ -274,21 +338,47 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   } else if (warp < 8) {
     // ================= epilogue =================
     const int e = warp - 4;
-    const int L = e * 32 + lane;                // TMEM lane = (plane in unit, row)
+    const int L = e * 32 + lane;                // TMEM lane = (row group, row)
     const int pl = L / T, row = L % T;
     const size_t plane_elems = (size_t)H * W;
     uint8_t* y1s = sm + Cfg::kOffY1;
     const int PR = W / E;                       // pieces per output row
     float st_s[3] = {0.f, 0.f, 0.f}, st_q[3] = {0.f, 0.f, 0.f};   // BatchNorm statistics of this thread's elements
     const bool want_stats = P.stats != nullptr;
+    int cur_c = c_first;
+    // write the statistics of channel `ch` gathered by this CTA (lanes -> warp -> the four epilogue warps)
+    auto flush_stats = [&](int ch) {
+      float* red = reinterpret_cast<float*>(y1s);   // staging is free between units
+#pragma unroll
+      for (int k2 = 0; k2 < 3; ++k2) {
+        float s = st_s[k2], q = st_q[k2];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if (lane == 0) { red[e * 6 + 2 * k2] = s; red[e * 6 + 2 * k2 + 1] = q; }
+        st_s[k2] = 0.f; st_q[k2] = 0.f;
+      }
+      named_bar_sync(1, 128);
+      // slot: T=64 -> split; multi-channel -> 0 for channels this CTA starts, 1.. when the channel began in an earlier CTA
+      int slot = slot0;
+      if (T != 64) {
+        const long long cta_of_first = ((long long)ch * upc) / P.per_cta;   // CTA holding the channel's first unit
+        slot = (int)(blockIdx.x - cta_of_first);
+      }
+      if (e == 0 && lane < 6 && slot < P.splits)
+        P.stats[((size_t)ch * P.splits + slot) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
+      named_bar_sync(1, 128);
+    };
     for (int i = 0; i < n_units; ++i) {
+      const long long gidx = g0 + i;
+      const int c = (int)(gidx / upc), u = (int)(gidx - (long long)c * upc);
+      if (want_stats && c != cur_c) { flush_stats(cur_c); cur_c = c; }
       const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
       mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
       uint32_t v[T];
 #pragma unroll
-      for (int g = 0; g < UPS; ++g) {               // row-group set / column band g: plane g*PPU + pl
-        const int n = PLANES * (u_begin + i) + g * PPU + pl;
+      for (int g = 0; g < UPS; ++g) {               // column band g: plane g*PPU + pl
+        const int n = PLANES * u + g * PPU + pl;
         const bool ok = (n < P.N) && (row < H);
         const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
         const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * Cfg::kAccCols + g * 3 * T;
@@ -306,7 +396,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
               float s = 0.f, q = 0.f;
 #pragma unroll
               for (int j = 0; j < T; ++j)
-                if (j < W) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))); s += f; q = fmaf(f, f, q); }
+                if (j < W) { const float f = __uint_as_float(v[j]); s += f; q = fmaf(f, f, q); }
               st_s[1 + br] += s; st_q[1 + br] += q;
             }
           }
@@ -324,7 +414,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
           float s = 0.f, q = 0.f;
 #pragma unroll
           for (int p = 0; p < T; ++p)
-            if (p < H) { const float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[p]))); s += f; q = fmaf(f, f, q); }
+            if (p < H) { const float f = __uint_as_float(v[p]); s += f; q = fmaf(f, f, q); }
           st_s[0] += s; st_q[0] += q;
         }
       }
@@ -334,7 +424,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       named_bar_sync(1, 128);
 #pragma unroll
       for (int g = 0; g < UPS; ++g) {
-        const int n = PLANES * (u_begin + i) + g * PPU + pl;
+        const int n = PLANES * u + g * PPU + pl;
         if ((n < P.N) && (row < H)) {
           __nv_bfloat16* yo = P.y1 + ((size_t)n * P.C + c) * plane_elems + (size_t)row * W;
           const uint32_t r = (uint32_t)(pl * T + row);
@@ -348,19 +438,26 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       }
       named_bar_sync(1, 128);                     // staging free for the next unit
     }
-    if (want_stats) {
-      // lanes -> warp -> the four epilogue warps, fixed order
-      float* red = reinterpret_cast<float*>(y1s);   // staging is free now
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float s = st_s[k], q = st_q[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-        if (lane == 0) { red[e * 6 + 2 * k] = s; red[e * 6 + 2 * k + 1] = q; }
+    if (want_stats && n_units > 0) flush_stats(cur_c);
+  } else if (warp == 10) {
+    // ================= Toeplitz builder: one set per channel of the range, NT sets in flight =================
+    float* w1s = reinterpret_cast<float*>(sm + Cfg::kOffW);   // [KL][5]
+    float* w2s = w1s + KL * 5;                                // [5][KL]
+    float* w3s = w2s + KL * 5;                                // [5][5]
+    for (int c = (NT == 1 ? c_last + 1 : c_first), k = 0; c <= c_last; ++c, ++k) {   // NT == 1: built by all threads below
+      const int set = k % NT;
+      mbar_wait(BAR(B_TP_EMPTY + set), ((k / NT) & 1) ^ 1);
+      uint8_t* tp = sm + Cfg::kOffToep + set * Cfg::kToepSet;
+      for (int i = lane; i < KL * 5; i += 32) {
+        w1s[i] = P.w1[(size_t)c * KL * 5 + i];
+        w2s[i] = P.w2[(size_t)c * KL * 5 + i];
       }
-      named_bar_sync(1, 128);
-      if (e == 0 && lane < 6)
-        P.stats[((size_t)c * P.splits + split) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
+      if (lane < 25) w3s[lane] = P.w3[(size_t)c * 25 + lane];
+      __syncwarp();
+      build_toeplitz<T>(tp, w1s, w2s, w3s, KL, pad, lane, 32);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_TP_FULL + set));
     }
   }
 
@@ -438,14 +535,37 @@ int tc_pick_splits(int C, int units) {
   return best;
 }
 
+// Work partition of the channel-walking kernels: grid size, items per CTA, statistics slots per channel.
+TcPlan tc_plan(int N, int C, int tile, int planes_per_unit) {
+  TcPlan p{};
+  p.units_per_c = (N + planes_per_unit - 1) / planes_per_unit;
+  if (tile == 64) {
+    p.splits = tc_pick_splits(C, p.units_per_c);
+    p.grid = C * p.splits;
+    p.per_cta = (p.units_per_c + p.splits - 1) / p.splits;
+  } else {
+    const long long total = (long long)C * p.units_per_c;
+    long long grid = sm_count();
+    if (grid > total) grid = total;
+    p.per_cta = (int)((total + grid - 1) / grid);
+    p.grid = (int)((total + p.per_cta - 1) / p.per_cta);
+    p.splits = (p.units_per_c + p.per_cta - 1) / p.per_cta + 1;   // CTAs that can touch one channel
+  }
+  return p;
+}
+
 template <int T, int CB, bool TMA>
 static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
   using Cfg = FwdCfg<T>;
-  P.units_per_c = (P.N + Cfg::PLANES - 1) / Cfg::PLANES;
-  P.splits = tc_pick_splits(P.C, P.units_per_c);
+  const TcPlan plan = tc_plan(P.N, P.C, T, Cfg::PLANES);
+  P.units_per_c = plan.units_per_c;
+  P.per_cta = plan.per_cta;
+  P.splits = plan.splits;
+  if (P.stats)   // not every slot of a channel is written in the multi-channel partition
+    SLAK_CUDA_TRY(cudaMemsetAsync(P.stats, 0, (size_t)P.C * plan.splits * 6 * sizeof(float), st));
   auto kern = lk3_fwd_tc_kernel<T, CB, TMA>;
   SLAK_SET_MAX_SMEM(kern, Cfg::kSmem);
-  kern<<<P.C * P.splits, kThreads, Cfg::kSmem, st>>>(map, P);
+  kern<<<plan.grid, kThreads, Cfg::kSmem, st>>>(map, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
@@ -453,14 +573,14 @@ static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
 int lk3_fwd_tc_splits(int N, int C, int H, int W) {
   const TcShape s = tc_shape(H, W);
   if (s.tile == 0) return 0;
-  const int planes = (128 / s.tile) * (64 / s.tile);
-  return tc_pick_splits(C, (N + planes - 1) / planes);
+  return tc_plan(N, C, s.tile, (128 / s.tile) * (64 / s.tile)).splits;
 }
 
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
                int N, int C, int H, int W, int KL, float* stats, cudaStream_t st) {
   SLAK_REQUIRE(lk3_tc_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   SLAK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SLAK_ERR_BAD_ARG, "x must be 16-byte aligned");
+  SLAK_REQUIRE((2 * KL * 5 + 25) * 4 <= 4096, SLAK_ERR_UNSUPPORTED, "kernel side %d too large", KL);
   const TcShape s = tc_shape(H, W);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));

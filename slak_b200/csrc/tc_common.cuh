@@ -141,6 +141,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 struct TcShape { int tile; int cb; bool tma; };
 TcShape tc_shape(int H, int W);
 int tc_pick_splits(int C, int units);
+// work partition of the channel-walking kernels over (channel, unit) items in channel-major order
+struct TcPlan { int grid; int per_cta; int units_per_c; int splits; };
+TcPlan tc_plan(int N, int C, int tile, int planes_per_unit);
 
 // ---- epilogue helpers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -286,6 +289,32 @@ __device__ __forceinline__ void load_plane_block(const PieceMap<CB>& pm, const u
       copy_piece_g2s<CB>(dst, src + (size_t)p * pm.W * 2 + b);
     }
   }
+}
+
+// 2-byte pieces cannot use cp.async: issue the loads of a batch of planes first, then the stores, so that the
+// global latency is paid once per batch instead of once per piece (7x7 planes: 49 pieces, 2 per lane)
+template <int NB>
+__device__ __forceinline__ void load_plane_blocks_cb2(const PieceMap<2>& pm, const uint8_t* const* src, uint32_t tile,
+                                                      const int* row0, const int* cb0, int nplanes, int lane) {
+  uint16_t val[NB][2];
+#pragma unroll
+  for (int q = 0; q < NB; ++q)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      val[q][k] = 0;
+      if (q < nplanes && k < pm.count && (lane + 32 * k) < pm.per_plane)
+        val[q][k] = *reinterpret_cast<const uint16_t*>(src[q] + pm.soff[k]);
+    }
+#pragma unroll
+  for (int q = 0; q < NB; ++q)
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (q < nplanes && k < pm.count && (lane + 32 * k) < pm.per_plane) {
+        const uint32_t p = pm.pb[k] >> 8, b = pm.pb[k] & 0xff;
+        const uint32_t row = (uint32_t)row0[q] + p;
+        const uint32_t dst = tile + row * 128 + ((((uint32_t)cb0[q] + (b >> 4)) ^ (row & 7)) << 4) + (b & 15);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "h"(val[q][k]) : "memory");
+      }
 }
 
 template <int NC>
