@@ -1,15 +1,18 @@
-// Depthwise data-gradient on the tensor cores (bf16 in/out, fp32 accumulate in TMEM):
+// Depthwise data-gradient on the tensor cores (bf16 in, fp32 accumulate in TMEM, bf16 or fp32 out):
 //     out = conv(in_t, W_t [KL x 5])  +  conv(in_n, W_n [5 x KN])  +  addend
 // with the taps optionally flipped (flip=1: backward_data of the forward convs,
 // backward_data_fp32.cu:199-263; dx = sum over the three branches of models/SLaK.py:89-100).
-// The same banded-Toeplitz formulation and tile classes (T = 64/32/16, 128/T stacked planes per
-// unit) as dwconv_tc_fwd.cu:
+// The same banded-Toeplitz formulation, tile classes (T = 64/32/16), units (one 128-row x 64-column
+// tile = 2/8/32 planes), persistent channel walk and Toeplitz builder warp as dwconv_tc_fwd.cu:
 //   natural path     D_n  [(plane,p), q] += IN_n [(plane,p+r-2), w] * Tn_r[q, w]
 //   transposed path  D_t^T[(plane,q), p] += IN_t^T[(plane,q+s-2), h] * Tt_s[p, h]
 // and the epilogue adds D_n + transpose(D_t^T) (+ addend rows read from global) before rounding.
 // dx of a Block needs two launches: (in_n = dy3, W_n = 5x5) -> tmp, then
 // (in_t = dy1, in_n = dy2, addend = tmp) -> dx; all three Toeplitz sets do not fit in shared memory
 // next to a multi-stage input pipeline at T = 64.
+//
+// Warp roles (352 threads): w0 loader | w1 MMA | w2-3 transposers (w2 owns TMEM) | w4-7 epilogue |
+// w8-9 extra loaders (cp.async path) | w10 Toeplitz builder.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
@@ -27,22 +30,25 @@ constexpr int kUnit = 128 * 128;
 constexpr int kPad = 1024;
 constexpr int kSlot = kPad + kUnit + kPad;     // 18 KB
 constexpr int kNumTransposerWarps = 2;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;
 template <int T> struct Cfg {
   static constexpr int PPU = 128 / T;
+  static constexpr int UPS = 64 / T;
+  static constexpr int PLANES = PPU * UPS;
   static constexpr int KSTEPS = T / 16;
-  static constexpr int kToep = 5 * T * 128;
-  static constexpr int kOffTn = 0;
-  static constexpr int kOffTt = kToep;
-  static constexpr int kOffXN = 2 * kToep;
+  static constexpr int NT = (T == 64) ? 1 : 2;
+  static constexpr int kToep = 5 * T * 128;                 // one path
+  static constexpr int kToepSet = 2 * kToep;                // Tn then Tt
+  static constexpr int kOffToep = 0;
+  static constexpr int kOffXN = NT * kToepSet;
   static constexpr int kOffXS = kOffXN + kNStages * kSlot;
   static constexpr int kOffXT = kOffXS + kSStages * kUnit;
-  static constexpr int kOffEx = kOffXT + kSlot;             // fp32 exchange [128][T]
-  static constexpr int kExBytes = 128 * T * 4 < 4096 ? 4096 : 128 * T * 4;
-  static constexpr int kOffBar = kOffEx + kExBytes;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
-  static constexpr int kAccCols = 2 * T;                    // D_n: cols 0..T-1, D_t^T: cols T..2T-1
-  static constexpr int kTmemCols = (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128 ? 128 : 256);
+  static constexpr int kOffEx = kOffXT + kSlot;             // fp32 exchange [128][64]
+  static constexpr int kOffW = kOffEx + 128 * 64 * 4;
+  static constexpr int kOffBar = kOffW + 4096;
+  static constexpr int kSmem = kOffBar + 1024 + 1024;
+  static constexpr int kAccCols = 2 * T * UPS;              // 128: per band D_n (T cols) then D_t^T (T cols)
+  static constexpr int kTmemCols = 256;
 };
 }  // namespace dg
 
@@ -54,34 +60,44 @@ struct DgradParams {
   const float* addend_f32;         // [N,C,H,W] fp32 or nullptr (e.g. the shortcut gradient of a Block)
   __nv_bfloat16* out;              // bf16 result, or nullptr when out_f32 is given
   float* out_f32;
-  int N, C, H, W, KL, KN, flip, has_t, splits, units_per_c;
+  int N, C, H, W, KL, KN, flip, has_t, splits, units_per_c, per_cta;
 };
 
-// same loader as the forward kernel (declared there as a template; repeated to keep the TU standalone)
-template <int T, int CB>
-__device__ __forceinline__ void dg_load_unit(const __nv_bfloat16* __restrict__ x, uint32_t tile, int n0, int c,
-                                             int N, int C, int H, int W, int lane) {
-  constexpr int PPU = 128 / T;
-  const int PR = (W * 2) / CB;
-  const int per_plane = H * PR;
-  const size_t plane_bytes = (size_t)H * W * 2;
-  for (int pl = 0; pl < PPU; ++pl) {
-    const int n = n0 + pl;
-    if (n >= N) break;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + ((size_t)n * C + c) * plane_bytes;
-    for (int e = lane; e < per_plane; e += 32) {
-      const int p = e / PR, j = e - p * PR;
-      const int row = pl * T + p;
-      const int b = j * CB;
-      const uint32_t dst = tile + row * 128 + ((((b >> 4) ^ (row & 7))) << 4) + (b & 15);
-      const uint8_t* s = src + (size_t)p * W * 2 + b;
-      if constexpr (CB >= 4) {
-        cp_async<CB>(dst, s);
-      } else {
-        const uint16_t val = *reinterpret_cast<const uint16_t*>(s);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst), "h"(val) : "memory");
-      }
+template <int T>
+__device__ __forceinline__ void build_toeplitz_pair(uint8_t* tp, const float* wts, const float* wns, int KL, int KN,
+                                                    bool has_t, int t0, int nthr) {
+  constexpr int CH = T / 8;
+  const int padn = KN / 2, padt = KL / 2;
+  for (int ch = t0; ch < 5 * T * CH; ch += nthr) {
+    const int s = ch / (T * CH), rem = ch - s * (T * CH), row = rem / CH, k8 = rem - row * CH;
+    float vn[8], vt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int tn = (k8 * 8 + j) - row + padn;
+      vn[j] = (tn >= 0 && tn < KN) ? wns[s * KN + tn] : 0.f;
+      const int tt = (k8 * 8 + j) - row + padt;
+      vt[j] = (has_t && tt >= 0 && tt < KL) ? wts[tt * 5 + s] : 0.f;
     }
+    const uint32_t off = s * (T * 128) + row * 128 + ((k8 ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(tp + off) =
+        make_uint4(pack_bf16(vn[0], vn[1]), pack_bf16(vn[2], vn[3]), pack_bf16(vn[4], vn[5]), pack_bf16(vn[6], vn[7]));
+    *reinterpret_cast<uint4*>(tp + 5 * T * 128 + off) =
+        make_uint4(pack_bf16(vt[0], vt[1]), pack_bf16(vt[2], vt[3]), pack_bf16(vt[4], vt[5]), pack_bf16(vt[6], vt[7]));
+  }
+}
+// taps of channel c -> fp32 staging, flipped when asked
+__device__ __forceinline__ void stage_taps(const DgradParams& P, int c, float* wts, float* wns, int t0, int nthr) {
+  const int KL = P.KL, KN = P.KN;
+  if (P.has_t)
+    for (int i = t0; i < KL * 5; i += nthr) {
+      const int t = i / 5, s = i - t * 5;
+      const int src = P.flip ? ((KL - 1 - t) * 5 + (4 - s)) : i;
+      wts[i] = P.wt[(size_t)c * KL * 5 + src];
+    }
+  for (int i = t0; i < 5 * KN; i += nthr) {
+    const int r = i / KN, t = i - r * KN;
+    const int src = P.flip ? ((4 - r) * KN + (KN - 1 - t)) : i;
+    wns[i] = P.wn[(size_t)c * 5 * KN + src];
   }
 }
 
@@ -90,26 +106,37 @@ __global__ void __launch_bounds__(dg::kThreads, 1)
 lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap nmap, DgradParams P) {
   using namespace dg;
   using Cf = Cfg<T>;
-  constexpr int PPU = Cf::PPU, KSTEPS = Cf::KSTEPS, E = CB / 2;
+  constexpr int PPU = Cf::PPU, UPS = Cf::UPS, PLANES = Cf::PLANES, KSTEPS = Cf::KSTEPS, NT = Cf::NT, E = CB / 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c = blockIdx.x / P.splits, split = blockIdx.x % P.splits;
-  const int u_begin = (int)(((long long)P.units_per_c * split) / P.splits);
-  const int u_end = (int)(((long long)P.units_per_c * (split + 1)) / P.splits);
-  const int n_units = u_end - u_begin;
+  const int upc = P.units_per_c;
+  long long g0, g1;
+  if (T == 64) {
+    const int c = blockIdx.x / P.splits, split = blockIdx.x % P.splits;
+    g0 = (long long)c * upc + ((long long)upc * split) / P.splits;
+    g1 = (long long)c * upc + ((long long)upc * (split + 1)) / P.splits;
+  } else {
+    const long long total = (long long)P.C * upc;
+    g0 = (long long)blockIdx.x * P.per_cta;
+    g1 = g0 + P.per_cta < total ? g0 + P.per_cta : total;
+    if (g0 > total) g0 = total;
+  }
+  const int n_units = (int)(g1 - g0);
+  const int c_first = n_units > 0 ? (int)(g0 / upc) : 0;
+  const int c_last = n_units > 0 ? (int)((g1 - 1) / upc) : -1;
   const int KL = P.KL, KN = P.KN, H = P.H, W = P.W;
   const bool has_t = P.has_t != 0;
 
   constexpr int B_N_FULL = 0, B_N_EMPTY = kNStages, B_S_FULL = 2 * kNStages, B_S_EMPTY = B_S_FULL + kSStages,
                 B_T_FULL = B_S_EMPTY + kSStages, B_T_EMPTY = B_T_FULL + 1, B_ACC_FULL = B_T_EMPTY + 1,
-                B_ACC_EMPTY = B_ACC_FULL + kAccBufs;
+                B_ACC_EMPTY = B_ACC_FULL + kAccBufs, B_TP_FULL = B_ACC_EMPTY + kAccBufs, B_TP_EMPTY = B_TP_FULL + NT;
   const uint32_t bar0 = base + Cf::kOffBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cf::kOffBar + 192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cf::kOffBar + 768);
 
   if (tid == 0) {
     for (int s = 0; s < kNStages; ++s) { mbar_init(BAR(B_N_FULL + s), 1); mbar_init(BAR(B_N_EMPTY + s), 1); }
@@ -117,45 +144,20 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     mbar_init(BAR(B_T_FULL), kNumTransposerWarps);
     mbar_init(BAR(B_T_EMPTY), 1);
     for (int a = 0; a < kAccBufs; ++a) { mbar_init(BAR(B_ACC_FULL + a), 1); mbar_init(BAR(B_ACC_EMPTY + a), 4); }
+    for (int s = 0; s < NT; ++s) { mbar_init(BAR(B_TP_FULL + s), 1); mbar_init(BAR(B_TP_EMPTY + s), 1); }
     mbar_fence_init();
     if (TMA) { tma_prefetch_desc(&nmap); if (has_t) tma_prefetch_desc(&tmap); }
   }
   {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < (Cf::kOffEx - Cf::kOffXN) / 16; i += kThreads) reinterpret_cast<uint4*>(sm + Cf::kOffXN)[i] = z;
-    // taps -> fp32 staging (exchange area), flipped when asked
-    float* wts = reinterpret_cast<float*>(sm + Cf::kOffEx);  // [KL][5]
-    float* wns = wts + KL * 5;                               // [5][KN]
-    if (has_t)
-      for (int i = tid; i < KL * 5; i += kThreads) {
-        const int t = i / 5, s = i - t * 5;
-        const int src = P.flip ? ((KL - 1 - t) * 5 + (4 - s)) : i;
-        wts[i] = P.wt[(size_t)c * KL * 5 + src];
-      }
-    for (int i = tid; i < 5 * KN; i += kThreads) {
-      const int r = i / KN, t = i - r * KN;
-      const int src = P.flip ? ((4 - r) * KN + (KN - 1 - t)) : i;
-      wns[i] = P.wn[(size_t)c * 5 * KN + src];
-    }
+  }
+  if (NT == 1 && n_units > 0) {   // single-channel range: every thread helps building the one Toeplitz set
+    float* wts = reinterpret_cast<float*>(sm + Cf::kOffW);
+    float* wns = wts + KL * 5;
+    stage_taps(P, c_first, wts, wns, tid, kThreads);
     __syncthreads();
-    const int padn = KN / 2, padt = KL / 2;
-    constexpr int CH = T / 8;
-    for (int ch = tid; ch < 5 * T * CH; ch += kThreads) {
-      const int s = ch / (T * CH), rem = ch - s * (T * CH), row = rem / CH, k8 = rem - row * CH;
-      float vn[8], vt[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int tn = (k8 * 8 + j) - row + padn;
-        vn[j] = (tn >= 0 && tn < KN) ? wns[s * KN + tn] : 0.f;
-        const int tt = (k8 * 8 + j) - row + padt;
-        vt[j] = (has_t && tt >= 0 && tt < KL) ? wts[tt * 5 + s] : 0.f;
-      }
-      const uint32_t off = s * (T * 128) + row * 128 + ((k8 ^ (row & 7)) << 4);
-      *reinterpret_cast<uint4*>(sm + Cf::kOffTn + off) =
-          make_uint4(pack_bf16(vn[0], vn[1]), pack_bf16(vn[2], vn[3]), pack_bf16(vn[4], vn[5]), pack_bf16(vn[6], vn[7]));
-      *reinterpret_cast<uint4*>(sm + Cf::kOffTt + off) =
-          make_uint4(pack_bf16(vt[0], vt[1]), pack_bf16(vt[2], vt[3]), pack_bf16(vt[4], vt[5]), pack_bf16(vt[6], vt[7]));
-    }
+    build_toeplitz_pair<T>(sm + Cf::kOffToep, wts, wns, KL, KN, has_t, tid, kThreads);
   }
   fence_proxy_async();
   if (warp == 2) tmem_alloc<Cf::kTmemCols>(smem_u32(tmem_slot));
@@ -164,12 +166,14 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const bool is_loader = (warp == 0) || (!TMA && warp >= 8);
+  const bool is_loader = (warp == 0) || (!TMA && (warp == 8 || warp == 9));
   if (is_loader) {
     if constexpr (TMA) {
       if (elect_one()) {
         for (int i = 0; i < n_units; ++i) {
-          const int n0 = PPU * (u_begin + i);
+          const long long g = g0 + i;
+          const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
+          const int n0 = PLANES * u;
           {
             const int st = i % kNStages, ph = (i / kNStages) & 1;
             mbar_wait(BAR(B_N_EMPTY + st), ph ^ 1);
@@ -191,17 +195,50 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
       }
     } else {
-      // three cp.async loader warps; loader j owns natural stage j; the source slots alternate per unit
+      // three cp.async loader warps; loader j owns natural slot j; the source slots alternate per unit
       const int lj = (warp == 0) ? 0 : (warp - 7);
+      PieceMap<CB> pm;
+      pm.init(H, W, lane);
+      const size_t plane_bytes = (size_t)H * W * 2;
       for (int i = lj; i < n_units; i += kNStages) {
-        const int n0 = PPU * (u_begin + i);
+        const long long g = g0 + i;
+        const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
+        const int n0 = PLANES * u;
         const int st = lj, ph = (i / kNStages) & 1;
         mbar_wait(BAR(B_N_EMPTY + st), ph ^ 1);
-        dg_load_unit<T, CB>(P.in_n, base + Cf::kOffXN + st * kSlot + kPad, n0, c, P.N, P.C, H, W, lane);
         const int ss = i % kSStages, sph = (i / kSStages) & 1;
-        if (has_t) {
-          mbar_wait(BAR(B_S_EMPTY + ss), sph ^ 1);
-          dg_load_unit<T, CB>(P.in_t, base + Cf::kOffXS + ss * kUnit, n0, c, P.N, P.C, H, W, lane);
+        if (has_t) mbar_wait(BAR(B_S_EMPTY + ss), sph ^ 1);
+        const uint32_t tn = base + Cf::kOffXN + st * kSlot + kPad;
+        const uint32_t ts = base + Cf::kOffXS + ss * kUnit;
+        if (CB == 2 && pm.count >= 0 && pm.count <= 2) {
+          for (int q0 = 0; q0 < PLANES; q0 += 8) {
+            const uint8_t* sn[8]; const uint8_t* stt[8]; int r0s[8], c0s[8];
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int q = q0 + j;
+              sn[j] = reinterpret_cast<const uint8_t*>(P.in_n); stt[j] = sn[j]; r0s[j] = 0; c0s[j] = 0;
+              if (q < PLANES && n0 + q < P.N) {
+                const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
+                sn[j] = reinterpret_cast<const uint8_t*>(P.in_n) + off;
+                stt[j] = has_t ? reinterpret_cast<const uint8_t*>(P.in_t) + off : sn[j];
+                r0s[j] = (q % PPU) * T; c0s[j] = (q / PPU) * (T / 8);
+                cnt = j + 1;
+              }
+            }
+            if constexpr (CB == 2) {
+              load_plane_blocks_cb2<8>(pm, sn, tn, r0s, c0s, cnt, lane);
+              if (has_t) load_plane_blocks_cb2<8>(pm, stt, ts, r0s, c0s, cnt, lane);
+            }
+          }
+        } else {
+          for (int q = 0; q < PLANES; ++q)
+            if (n0 + q < P.N) {
+              const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
+              load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.in_n) + off, tn, (q % PPU) * T, (q / PPU) * (T / 8), lane);
+              if (has_t)
+                load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.in_t) + off, ts, (q % PPU) * T, (q / PPU) * (T / 8), lane);
+            }
         }
         cp_async_commit();
         cp_async_wait_all();
@@ -217,31 +254,43 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ================= MMA issuer =================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, T);
+      int cur_c = -1, k = -1;
       for (int i = 0; i < n_units; ++i) {
+        const int c = (int)((g0 + i) / upc);
+        if (c != cur_c) {
+          if (k >= 0) umma_commit(BAR(B_TP_EMPTY + (k % NT)));
+          cur_c = c; ++k;
+          if (NT > 1) mbar_wait(BAR(B_TP_FULL + (k % NT)), (k / NT) & 1);
+        }
+        const uint32_t toep = base + Cf::kOffToep + (k % NT) * Cf::kToepSet;
         const int st = i % kNStages, ph = (i / kNStages) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
         mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);
         mbar_wait(BAR(B_N_FULL + st), ph);
         tc_fence_after();
         const uint32_t xn = base + Cf::kOffXN + st * kSlot + kPad;
-        const uint32_t dn = tmem + ab * Cf::kAccCols;
+        const uint32_t acc = tmem + ab * Cf::kAccCols;
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
+        for (int g = 0; g < UPS; ++g)
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k)
-            umma_bf16(dn, umma_desc_k_sw128(xn + (r - 2) * 128 + k * 32, 0),
-                      umma_desc_k_sw128(base + Cf::kOffTn + r * (T * 128) + k * 32, 0), idesc, (r | k) != 0);
+          for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk)
+              umma_bf16(acc + g * 2 * T, umma_desc_k_sw128(xn + (r - 2) * 128 + g * (T * 2) + kk * 32, 0),
+                        umma_desc_k_sw128(toep + r * (T * 128) + kk * 32, 0), idesc, (r | kk) != 0);
         umma_commit(BAR(B_N_EMPTY + st));
         if (has_t) {
           mbar_wait(BAR(B_T_FULL), i & 1);
           tc_fence_after();
           const uint32_t xt = base + Cf::kOffXT + kPad;
 #pragma unroll
-          for (int s = 0; s < 5; ++s)
+          for (int g = 0; g < UPS; ++g)
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16(dn + T, umma_desc_k_sw128(xt + (s - 2) * 128 + k * 32, 0),
-                        umma_desc_k_sw128(base + Cf::kOffTt + s * (T * 128) + k * 32, 0), idesc, (s | k) != 0);
+            for (int s = 0; s < 5; ++s)
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk)
+                umma_bf16(acc + g * 2 * T + T, umma_desc_k_sw128(xt + (s - 2) * 128 + g * (T * 2) + kk * 32, 0),
+                          umma_desc_k_sw128(toep + Cf::kToep + s * (T * 128) + kk * 32, 0), idesc, (s | kk) != 0);
           umma_commit(BAR(B_T_EMPTY));
         }
         umma_commit(BAR(B_ACC_FULL + ab));
@@ -260,12 +309,13 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t xs = base + Cf::kOffXS + st * kUnit;
         const uint32_t xt = base + Cf::kOffXT + kPad;
 #pragma unroll 4
-        for (int it = tw; it < T / 2; it += kNumTransposerWarps) {
+        for (int it = tw; it < 32; it += kNumTransposerWarps) {
           const int blk = 4 * it + m;
-          const int pl = blk / (NB * NB), rem = blk - pl * (NB * NB);
+          const int g = blk / (2 * T), rem0 = blk - g * (2 * T);
+          const int pl = rem0 / (NB * NB), rem = rem0 - pl * (NB * NB);
           const int bi = rem / NB, bj = rem - bi * NB;
-          const uint32_t src = xs + (pl * T + 8 * bi + kk) * 128 + ((bj ^ kk) << 4);
-          const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + ((bi ^ kk) << 4);
+          const uint32_t src = xs + (pl * T + 8 * bi + kk) * 128 + (((g * NB + bj) ^ kk) << 4);
+          const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + (((g * NB + bi) ^ kk) << 4);
           uint32_t r0, r1, r2, r3;
           ldmatrix_x4_trans(src, r0, r1, r2, r3);
           stmatrix_x4(dst, r0, r1, r2, r3);
@@ -284,58 +334,81 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int L = e * 32 + lane;
     const int pl = L / T, row = L % T;
     const size_t plane_elems = (size_t)H * W;
-    float* ex = reinterpret_cast<float*>(sm + Cf::kOffEx);
+    float* ex = reinterpret_cast<float*>(sm + Cf::kOffEx);   // [128 rows][64 floats]: band g uses floats [g*T, g*T+T)
     const int PR = W / E;
-    constexpr int XM = T / 4 - 1;               // float4-chunk XOR mask of the exchange rows
+    constexpr int XM = T / 4 - 1;               // float4-chunk XOR mask inside a band
     for (int i = 0; i < n_units; ++i) {
+      const long long gidx = g0 + i;
+      const int c = (int)(gidx / upc), u = (int)(gidx - (long long)c * upc);
       const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
-      const int n = PPU * (u_begin + i) + pl;
-      const bool ok = (n < P.N) && (row < H);
-      const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
       mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
-      const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * Cf::kAccCols;
       uint32_t v[T];
       if (has_t) {
-        // D_t^T: this thread holds column `row`(=q) over p -> exchange[(pl,p)][q] (float4-chunk XOR swizzle)
-        tmem_ld_cols<T>(t0 + T, v);
-        tmem_ld_wait();
+        // D_t^T: this thread holds column `row`(=q) over p -> exchange[(pl,p)][band g, q] (float4-chunk XOR swizzle)
 #pragma unroll
-        for (int p = 0; p < T; ++p) {
-          const int chunk = (row >> 2) ^ (p & XM);
-          ex[(pl * T + p) * T + chunk * 4 + (row & 3)] = __uint_as_float(v[p]);
-        }
-      }
-      tmem_ld_cols<T>(t0, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));
-      if (has_t) {
-        named_bar_sync(1, 128);
+        for (int g = 0; g < UPS; ++g) {
+          tmem_ld_cols<T>(tmem + ((uint32_t)(e * 32) << 16) + ab * Cf::kAccCols + g * 2 * T + T, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int ck = 0; ck < T / 4; ++ck) {
-          const float4 t = *reinterpret_cast<const float4*>(&ex[(pl * T + row) * T + ((ck ^ (row & XM)) << 2)]);
-          v[4 * ck + 0] = __float_as_uint(__uint_as_float(v[4 * ck + 0]) + t.x);
-          v[4 * ck + 1] = __float_as_uint(__uint_as_float(v[4 * ck + 1]) + t.y);
-          v[4 * ck + 2] = __float_as_uint(__uint_as_float(v[4 * ck + 2]) + t.z);
-          v[4 * ck + 3] = __float_as_uint(__uint_as_float(v[4 * ck + 3]) + t.w);
-        }
-        named_bar_sync(1, 128);        // exchange free for the next unit
-      }
-      if (ok) {
-#pragma unroll
-        for (int j = 0; j < T / E; ++j)
-          if (j < PR) {
-            if (P.addend) add_bf16_piece<E>(v + j * E, P.addend + rbase + j * E);
-            if (P.out_f32) {
-              if (P.addend_f32) add_f32_piece<E>(v + j * E, P.addend_f32 + rbase + j * E);
-              store_f32_piece<E>(P.out_f32 + rbase + j * E, v + j * E);
-            } else {
-              store_bf16_piece<E>(P.out + rbase + j * E, v + j * E);
-            }
+          for (int p = 0; p < T; ++p) {
+            const int chunk = (row >> 2) ^ (p & XM);
+            ex[(pl * T + p) * 64 + g * T + chunk * 4 + (row & 3)] = __uint_as_float(v[p]);
           }
+        }
+        named_bar_sync(1, 128);
       }
+#pragma unroll
+      for (int g = 0; g < UPS; ++g) {
+        const int n = PLANES * u + g * PPU + pl;
+        const bool ok = (n < P.N) && (row < H);
+        const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
+        tmem_ld_cols<T>(tmem + ((uint32_t)(e * 32) << 16) + ab * Cf::kAccCols + g * 2 * T, v);
+        tmem_ld_wait();
+        if (g == UPS - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));
+        }
+        if (has_t) {
+#pragma unroll
+          for (int ck = 0; ck < T / 4; ++ck) {
+            const float4 t = *reinterpret_cast<const float4*>(&ex[(pl * T + row) * 64 + g * T + ((ck ^ (row & XM)) << 2)]);
+            v[4 * ck + 0] = __float_as_uint(__uint_as_float(v[4 * ck + 0]) + t.x);
+            v[4 * ck + 1] = __float_as_uint(__uint_as_float(v[4 * ck + 1]) + t.y);
+            v[4 * ck + 2] = __float_as_uint(__uint_as_float(v[4 * ck + 2]) + t.z);
+            v[4 * ck + 3] = __float_as_uint(__uint_as_float(v[4 * ck + 3]) + t.w);
+          }
+        }
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < T / E; ++j)
+            if (j < PR) {
+              if (P.addend) add_bf16_piece<E>(v + j * E, P.addend + rbase + j * E);
+              if (P.out_f32) {
+                if (P.addend_f32) add_f32_piece<E>(v + j * E, P.addend_f32 + rbase + j * E);
+                store_f32_piece<E>(P.out_f32 + rbase + j * E, v + j * E);
+              } else {
+                store_bf16_piece<E>(P.out + rbase + j * E, v + j * E);
+              }
+            }
+        }
+      }
+      if (has_t) named_bar_sync(1, 128);        // exchange free for the next unit
+    }
+  } else if (warp == 10) {
+    // ================= Toeplitz builder (multi-channel classes) =================
+    float* wts = reinterpret_cast<float*>(sm + Cf::kOffW);
+    float* wns = wts + KL * 5;
+    for (int c = (NT == 1 ? c_last + 1 : c_first), k = 0; c <= c_last; ++c, ++k) {
+      const int set = k % NT;
+      mbar_wait(BAR(B_TP_EMPTY + set), ((k / NT) & 1) ^ 1);
+      stage_taps(P, c, wts, wns, lane, 32);
+      __syncwarp();
+      build_toeplitz_pair<T>(sm + Cf::kOffToep + set * Cf::kToepSet, wts, wns, KL, KN, has_t, lane, 32);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_TP_FULL + set));
     }
   }
 
@@ -347,11 +420,13 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 template <int T, int CB, bool TMA>
 static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParams& P, cudaStream_t st) {
   using Cf = dg::Cfg<T>;
-  P.units_per_c = (P.N + Cf::PPU - 1) / Cf::PPU;
-  P.splits = tc_pick_splits(P.C, P.units_per_c);
+  const TcPlan plan = tc_plan(P.N, P.C, T, Cf::PLANES);
+  P.units_per_c = plan.units_per_c;
+  P.per_cta = plan.per_cta;
+  P.splits = plan.splits;
   auto kern = lk_dgrad_tc_kernel<T, CB, TMA>;
   SLAK_SET_MAX_SMEM(kern, Cf::kSmem);
-  kern<<<P.C * P.splits, dg::kThreads, Cf::kSmem, st>>>(mt, mn, P);
+  kern<<<plan.grid, dg::kThreads, Cf::kSmem, st>>>(mt, mn, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
@@ -362,6 +437,7 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
                cudaStream_t st) {
   const TcShape s = tc_shape(H, W);
   SLAK_REQUIRE(s.tile != 0, SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
+  SLAK_REQUIRE((KL * 5 + 5 * KN) * 4 <= 4096, SLAK_ERR_UNSUPPORTED, "kernel side %d too large", KL);
   CUtensorMap mt, mn;
   memset(&mt, 0, sizeof(mt)); memset(&mn, 0, sizeof(mn));
   if (s.tma) {
@@ -387,7 +463,7 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
 // shapes covered by the tensor-core dgrad/wgrad kernels: the same set as the forward
 bool lk3_bwd_tc_supported(int N, int C, int H, int W, int KL) {
   (void)N; (void)C;
-  return tc_shape(H, W).tile != 0 && (KL & 1) && KL >= 5 && KL <= 129;
+  return tc_shape(H, W).tile != 0 && (KL & 1) && KL >= 5 && KL <= 99;
 }
 
 }  // namespace tc

@@ -518,7 +518,7 @@ TcShape tc_shape(int H, int W) {
 
 bool lk3_tc_supported(int N, int C, int H, int W, int KL) {
   (void)N; (void)C;
-  return tc_shape(H, W).tile != 0 && (KL & 1) && KL >= 5 && KL <= 129;
+  return tc_shape(H, W).tile != 0 && (KL & 1) && KL >= 5 && KL <= 99;
 }
 
 int tc_pick_splits(int C, int units) {
