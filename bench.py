@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    p.add_argument("--graph-multi", action="store_true", help="also capture the step in a CUDA graph when N > 1")
     return p.parse_args()
 
 
@@ -253,7 +254,10 @@ def run_ours(args):
 
     graph, static_loss, graph_note = None, None, "eager (no CUDA graph)"
     prof_events = []
-    if not args.no_graph:
+    use_graph = not args.no_graph and (world == 1 or args.graph_multi)
+    if not use_graph and world > 1:
+        graph_note = "eager launches (CUDA-graph capture of the NCCL all-reduces is opt-in: --graph-multi)"
+    if use_graph:
         try:
             ops.profile_reset(dict(HEADLINE, external_events=True))
             l_before = ops.launch_count()
