@@ -44,7 +44,6 @@ def parse():
     p.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    p.add_argument("--graph-multi", action="store_true", help="also capture the step in a CUDA graph when N > 1")
     return p.parse_args()
 
 
@@ -101,13 +100,32 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # the reference's CPU path (oracle restatement, fp32, nn.Conv2d semantics) -- checker / baseline only
 # ---------------------------------------------------------------------------------------
+def host_cores():
+    """Threads the CPU arm may really use: the scheduler affinity, clipped by the cgroup CPU quota when the
+    container has one (spinning 128 OpenMP threads on a smaller quota is what makes a CPU run crawl), or
+    SLAK_CPU_THREADS when set."""
+    if os.environ.get("SLAK_CPU_THREADS"):
+        return max(1, int(os.environ["SLAK_CPU_THREADS"]))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_training_step_factory(width_factor, batch):
     """Returns (step_fn, cores): one fwd+bwd+AdamW step of SLaK-T on the host cores through the
     oracle's functional restatement of models/SLaK.py (F.conv2d depthwise, train-mode BN)."""
     from oracle import slak_model as omodel
     from slak_b200 import slak
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = host_cores()
+    torch.set_num_threads(cores)     # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     torch.manual_seed(0)
     slak.use_sync_bn = False
     net = slak.SLaK_tiny(kernel_size=KERNEL_SIZE, Decom=True, bn=True, drop_path_rate=0.0,
@@ -254,15 +272,14 @@ def run_ours(args):
 
     graph, static_loss, graph_note = None, None, "eager (no CUDA graph)"
     prof_events = []
-    use_graph = not args.no_graph and (world == 1 or args.graph_multi)
-    if not use_graph and world > 1:
-        graph_note = "eager launches (CUDA-graph capture of the NCCL all-reduces is opt-in: --graph-multi)"
+    use_graph = not args.no_graph
     if use_graph:
         try:
             ops.profile_reset(dict(HEADLINE, external_events=True))
             l_before = ops.launch_count()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread's event queries must not invalidate this thread's capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = step_eager()
             prof_events = list(ops._prof["events"])
             launches_per_step = ops.launch_count() - l_before
@@ -273,6 +290,13 @@ def run_ours(args):
             ops.profile_reset(None)
             torch.cuda.synchronize()
             graph_note = f"eager (CUDA graph capture failed: {type(ex).__name__})"
+            print(f"[bench] rank {rank}: graph capture failed: {ex!r}", file=sys.stderr, flush=True)
+        if world > 1:                # every rank must replay, or none: the captured collectives have to pair up
+            ok = torch.tensor([1 if graph is not None else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and graph is not None:
+                graph, static_loss = None, None
+                graph_note = "eager (CUDA graph capture failed on another rank)"
 
     def run_step():
         if graph is not None:
@@ -381,8 +405,16 @@ def run_ours(args):
                           f"oracle/slak_model.py (F.conv2d depthwise, fp32), {cores} threads"}
         print(json.dumps(line), flush=True)
     if dist is not None:
+        # tear down without ncclCommDestroy: with the step graph (which holds the captured all-reduces) alive the
+        # communicator teardown blocks forever; the process exits right after, which frees everything
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        if graph is not None:
+            graph.reset()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
