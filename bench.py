@@ -41,7 +41,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     p.add_argument("--width-factor", type=float, default=1.0)
-    p.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step")
+    p.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return p.parse_args()
@@ -246,6 +246,9 @@ def run_ours(args):
             g_.copy_(f_)
 
     def step_eager():
+        # optimizer.zero_grad() as in engine.py:74-86 (set_to_none is the torch default): backward then writes fresh gradients instead of
+        # accumulating into zeroed ones; under graph capture they live in the graph's private pool
+        opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = net(x_dev)
             loss = F.cross_entropy(out.float(), y_dev)
@@ -253,7 +256,6 @@ def run_ours(args):
         if world > 1:
             allreduce_grads()
         opt.step()
-        opt.zero_grad(set_to_none=False)
         return loss
 
     def barrier():

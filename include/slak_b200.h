@@ -178,6 +178,25 @@ SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, 
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * LayerNorm over the channels of an NCHW tensor: the "channels_first" branch of
+ * LayerNorm.forward (models/SLaK.py:256-261), used by the stem and the three
+ * downsampling layers (models/SLaK.py:192-203) on either side of the Blocks.
+ *     y = w[c] * (x - mean_c x) / sqrt(mean_c (x - mean_c x)^2 + eps) + b[c]
+ * x, y and the incoming gradient g may each be SLAK_F32 or SLAK_BF16; mean and
+ * rstd ([N*HW] fp32, may both be NULL in the forward when no backward follows)
+ * are what the backward needs besides x.  The backward writes dx (dtype of x),
+ * dw and db ([C] fp32, overwritten); `part` is a workspace of
+ * slak_layernorm2d_bwd_parts(N, HW) * 2 * C floats.
+ * ------------------------------------------------------------------------- */
+SLAK_API int slak_layernorm2d_fwd(const void* x, int x_dtype, const float* w, const float* b, float eps,
+                                  void* y, int y_dtype, float* mean, float* rstd, int N, int C, int HW,
+                                  void* stream);
+SLAK_API int slak_layernorm2d_bwd_parts(int N, int HW);
+SLAK_API int slak_layernorm2d_bwd(const void* g, int g_dtype, const void* x, int x_dtype, const float* w,
+                                  const float* mean, const float* rstd, void* dx, float* part, float* dw,
+                                  float* db, int N, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Sparse-mask engine (sparse_core.py:316-333, funcs.py:107-114).
  * ------------------------------------------------------------------------- */
 

@@ -261,10 +261,16 @@ residual_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restr
 // MLP backward glue: dh = da * gelu'(h) (exact erf GELU), plus per-CTA column sums of dh
 // (bias gradient of pwconv1).  da, h, dh: [rows][K] bf16 row-major, K % 8 == 0.
 // ------------------------------------------------------------------------------------------
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x).  Phi through erf's rational approximation (Abramowitz & Stegun 7.1.26,
+// |error| <= 1.5e-7, far below the bf16 rounding of the result): it shares the one exponential with phi, which
+// keeps this kernel on the memory side of its roofline (erff() alone costs more than the two loads and the store)
 __device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float e = __expf(-0.5f * x * x);                       // exp(-z^2), z = |x| / sqrt(2)
+  const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float erfz = fmaf(-poly, e, 1.f);                      // erf(|x| / sqrt(2))
+  const float cdf = 0.5f + copysignf(0.5f * erfz, x);
+  return fmaf(x, 0.39894228040143268f * e, cdf);
 }
 __global__ void __launch_bounds__(kThreads)
 gelu_bwd_bias_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ h,
@@ -283,15 +289,36 @@ gelu_bwd_bias_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* 
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] = 0.f;
     if (vec < nv && rsub < rsubs) {
-      for (long long r = r0 + rsub; r < r1; r += rsubs) {
-        const size_t off = (size_t)r * K + (size_t)vec * 8;
-        float a[8], x[8], o[8];
-        ld_bf16<8>(da + off, a); ld_bf16<8>(h + off, x);
+      constexpr int U = 4;                       // rows in flight per thread: 8 x 16-byte loads before the first use
+      for (long long r = r0 + rsub; r < r1; r += (long long)U * rsubs) {
+        uint4 ra[U], rx[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = a[k] * gelu_grad(x[k]);
-        st_bf16<8>(dh + off, o);
+        for (int u = 0; u < U; ++u) {
+          const long long rr = r + (long long)u * rsubs;
+          if (rr < r1) {
+            const size_t off = (size_t)rr * K + (size_t)vec * 8;
+            ra[u] = *reinterpret_cast<const uint4*>(da + off);
+            rx[u] = *reinterpret_cast<const uint4*>(h + off);
+          }
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] += __bfloat162float(__float2bfloat16_rn(o[k]));
+        for (int u = 0; u < U; ++u) {
+          const long long rr = r + (long long)u * rsubs;
+          if (rr < r1) {
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ra[u]);
+            const __nv_bfloat162* px = reinterpret_cast<const __nv_bfloat162*>(&rx[u]);
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 a2 = __bfloat1622float2(pa[k]), x2 = __bfloat1622float2(px[k]);
+              o[2 * k] = a2.x * gelu_grad(x2.x);
+              o[2 * k + 1] = a2.y * gelu_grad(x2.y);
+            }
+            st_bf16<8>(dh + (size_t)rr * K + (size_t)vec * 8, o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] += __bfloat162float(__float2bfloat16_rn(o[k]));
+          }
+        }
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) red[(size_t)rsub * K + vec * 8 + k] = s[k];
@@ -308,7 +335,17 @@ gelu_bwd_bias_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------
 // backward: LayerNorm backward + BatchNorm reductions.  part layout per CTA: [6][C] =
 //   dlnw, dlnb, S0 = sum du, S1..S3 = sum du*y_i
+// Per tile: (1) stage u = sum_i scale_i*y_i + shift (fp32 [C][pitch]), the incoming gradient rows (bf16
+// [PIX][ge], ge/2 odd so that a column walk is bank-conflict free), mu and rstd -- every global load of the tile is
+// in flight at once; (2) one warp per pixel reduces mean_c(g*w) and mean_c(g*w*xhat) from shared memory; (3) one
+// thread per (channel, VP pixels) forms du, stores it (NCHW) and accumulates all six per-channel sums, which a
+// segmented shuffle folds into shared accumulators owned by exactly one lane each (deterministic).
 // ------------------------------------------------------------------------------------------
+__host__ __device__ inline int ln_bwd_gpitch(int C) {   // bf16 elements per staged gradient row
+  int ge = (C + 1) & ~1;
+  if (((ge / 2) & 1) == 0) ge += 2;
+  return ge;
+}
 template <int VP>
 __global__ void __launch_bounds__(kThreads)
 bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16* __restrict__ y1,
@@ -318,24 +355,43 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
                       __nv_bfloat16* __restrict__ du, float* __restrict__ part /*[grid][6][C]*/, Geo g) {
   extern __shared__ float tile[];
   const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
-  float* accw = tile + (size_t)C * pitch;      // [kWarps][2][C]  dlnw, dlnb per warp
-  float* accs = accw + kWarps * 2 * C;         // [4][C]          S0..S3 (each channel owned by one warp)
-  float* lnw_s = accs + 4 * C;                 // [C]
+  const int ge = ln_bwd_gpitch(C);
+  float* accs = tile + (size_t)C * pitch;      // [6][C]
+  float* lnw_s = accs + 6 * C;                 // [C]
+  float* mus = lnw_s + C;                      // [PIX] mu, rstd, m1, m2
+  float* rs = mus + PIX;
+  float* m1s = rs + PIX;
+  float* m2s = m1s + PIX;
+  __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(m2s + PIX);   // [PIX][ge]
+  const uint32_t* gs32 = reinterpret_cast<const uint32_t*>(gs);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vec_per_row = PIX / VP;
-  for (int i = tid; i < kWarps * 2 * C + 4 * C; i += kThreads) accw[i] = 0.f;
+  for (int i = tid; i < 6 * C; i += kThreads) accs[i] = 0.f;
   for (int i = tid; i < C; i += kThreads) lnw_s[i] = lnw[i];
-  // register path: each lane owns channel pairs (2*lane + 64k, +1), k < KM, for every pixel its warp visits
-  constexpr int KM = 12;
-  const bool regpath = ((C & 1) == 0) && (C <= 64 * KM);
-  float aw0[KM], aw1[KM], ab0[KM], ab1[KM];
-#pragma unroll
-  for (int k = 0; k < KM; ++k) { aw0[k] = aw1[k] = ab0[k] = ab1[k] = 0.f; }
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
     const int npix = min(PIX, HW - p0);
     __syncthreads();
-    // phase 1: recompute u = sum_i scale_i*y_i + shift
+    // phase 1a: gradient rows of the tile: one contiguous run of npix*C bf16 in NHWC
+    {
+      const __nv_bfloat16* gsrc = dxn + ((size_t)n * HW + p0) * C;
+      if ((C & 7) == 0 && (reinterpret_cast<uintptr_t>(dxn) & 15) == 0) {
+        const int nvec = npix * C / 8;
+        for (int v = tid; v < nvec; v += kThreads) {
+          const uint4 r = *reinterpret_cast<const uint4*>(gsrc + (size_t)v * 8);
+          const int e = v * 8, j = e / C, c = e - j * C;
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(gs + (size_t)j * ge + c);
+          d32[0] = r.x; d32[1] = r.y; d32[2] = r.z; d32[3] = r.w;
+        }
+      } else {
+        for (int e = tid; e < npix * C; e += kThreads) {
+          const int j = e / C, c = e - j * C;
+          gs[(size_t)j * ge + c] = gsrc[e];
+        }
+      }
+      for (int j = tid; j < npix; j += kThreads) { mus[j] = mu[(size_t)n * HW + p0 + j]; rs[j] = rstd[(size_t)n * HW + p0 + j]; }
+    }
+    // phase 1b: recompute u = sum_i scale_i*y_i + shift
     for (int idx = tid; idx < C * vec_per_row; idx += kThreads) {
       const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
       const int j = jv * VP;
@@ -349,59 +405,52 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
       }
     }
     __syncthreads();
-    // phase 2: per pixel LayerNorm backward, du overwrites u in the tile
+    // phase 2: per pixel m1 = mean_c(g*w), m2 = mean_c(g*w*xhat)
     for (int j = warp; j < npix; j += kWarps) {
-      const size_t pix = (size_t)n * HW + p0 + j;
-      const float m = mu[pix], r = rstd[pix];
-      const __nv_bfloat16* gp = dxn + pix * C;
+      const float m = mus[j], r = rs[j];
       float s1 = 0.f, s2 = 0.f;
-      if (regpath) {
-        uint32_t graw[KM];
-#pragma unroll
-        for (int k = 0; k < KM; ++k) {
-          const int c = 2 * lane + 64 * k;
-          graw[k] = 0u;
-          if (c < C) {
-            graw[k] = *reinterpret_cast<const uint32_t*>(gp + c);
-            const float2 gx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&graw[k]));
-            const float xh0 = (tile[c * pitch + j] - m) * r, xh1 = (tile[(c + 1) * pitch + j] - m) * r;
-            const float gg0 = gx.x * lnw_s[c], gg1 = gx.y * lnw_s[c + 1];
-            s1 += gg0 + gg1;
-            s2 = fmaf(gg0, xh0, fmaf(gg1, xh1, s2));
-            aw0[k] = fmaf(gx.x, xh0, aw0[k]); aw1[k] = fmaf(gx.y, xh1, aw1[k]);
-            ab0[k] += gx.x; ab1[k] += gx.y;
-          }
+      if ((C & 1) == 0) {
+        for (int cw = lane; cw < C / 2; cw += 32) {
+          const uint32_t raw = gs32[(size_t)j * (ge / 2) + cw];
+          const float2 gx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+          const int c = 2 * cw;
+          const float xh0 = (tile[c * pitch + j] - m) * r, xh1 = (tile[(c + 1) * pitch + j] - m) * r;
+          const float gg0 = gx.x * lnw_s[c], gg1 = gx.y * lnw_s[c + 1];
+          s1 += gg0 + gg1;
+          s2 = fmaf(gg0, xh0, fmaf(gg1, xh1, s2));
         }
-        const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
-#pragma unroll
-        for (int k = 0; k < KM; ++k) {
-          const int c = 2 * lane + 64 * k;
-          if (c < C) {
-            const float2 gx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&graw[k]));
-            const float xh0 = (tile[c * pitch + j] - m) * r, xh1 = (tile[(c + 1) * pitch + j] - m) * r;
-            tile[c * pitch + j] = r * (gx.x * lnw_s[c] - m1 - xh0 * m2);
-            tile[(c + 1) * pitch + j] = r * (gx.y * lnw_s[c + 1] - m1 - xh1 * m2);
-          }
+      } else {
+        for (int c = lane; c < C; c += 32) {
+          const float gg = bf(gs[(size_t)j * ge + c]) * lnw_s[c];
+          s1 += gg;
+          s2 = fmaf(gg, (tile[c * pitch + j] - m) * r, s2);
         }
-        continue;
       }
-      for (int c = lane; c < C; c += 32) {
-        const float gx = bf(gp[c]);
-        const float xh = (tile[c * pitch + j] - m) * r;
-        const float gg = gx * lnw[c];
-        s1 += gg; s2 = fmaf(gg, xh, s2);
-        accw[(warp * 2 + 0) * C + c] = fmaf(gx, xh, accw[(warp * 2 + 0) * C + c]);
-        accw[(warp * 2 + 1) * C + c] += gx;
-      }
-      const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
-      for (int c = lane; c < C; c += 32) {
-        const float xh = (tile[c * pitch + j] - m) * r;
-        const float gg = bf(gp[c]) * lnw[c];
-        tile[c * pitch + j] = r * (gg - m1 - xh * m2);
-      }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) { m1s[j] = s1 / C; m2s[j] = s2 / C; }
     }
     __syncthreads();
-    // phase 3: write du (NCHW bf16) and accumulate the BatchNorm reductions; one warp per channel
+    // phase 3: du (NCHW bf16) and the six per-channel sums
+    auto body = [&](int c, int j, float* a) {
+      const size_t off = ((size_t)n * C + c) * HW + p0 + j;
+      float d[VP], q1[VP], q2[VP], q3[VP];
+      ld_bf16<VP>(y1 + off, q1); ld_bf16<VP>(y2 + off, q2); ld_bf16<VP>(y3 + off, q3);
+      const float w = lnw_s[c];
+#pragma unroll
+      for (int k = 0; k < VP; ++k) {
+        const float r = rs[j + k];
+        const float xh = (tile[c * pitch + j + k] - mus[j + k]) * r;
+        const float gv = bf(gs[(size_t)(j + k) * ge + c]);
+        d[k] = r * (gv * w - m1s[j + k] - xh * m2s[j + k]);
+        a[0] = fmaf(gv, xh, a[0]); a[1] += gv;
+      }
+      st_bf16<VP>(du + off, d);
+#pragma unroll
+      for (int k = 0; k < VP; ++k) {
+        const float dr = __bfloat162float(__float2bfloat16_rn(d[k]));   // the value BN backward will see
+        a[2] += dr; a[3] = fmaf(dr, q1[k], a[3]); a[4] = fmaf(dr, q2[k], a[4]); a[5] = fmaf(dr, q3[k], a[5]);
+      }
+    };
     if (vec_per_row <= 32) {
       // vec_per_row (a power of two) consecutive lanes share a channel: segmented shuffle reduction
       const int total = C * vec_per_row;
@@ -409,70 +458,36 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
         const int idx = idx0 + tid;
         const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
         const int j = jv * VP;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (idx < total && j < npix) {
-          const size_t off = ((size_t)n * C + c) * HW + p0 + j;
-          float d[VP], q1[VP], q2[VP], q3[VP];
-#pragma unroll
-          for (int k = 0; k < VP; ++k) d[k] = tile[c * pitch + j + k];
-          st_bf16<VP>(du + off, d);
-          ld_bf16<VP>(y1 + off, q1); ld_bf16<VP>(y2 + off, q2); ld_bf16<VP>(y3 + off, q3);
-#pragma unroll
-          for (int k = 0; k < VP; ++k) {
-            const float dr = __bfloat162float(__float2bfloat16_rn(d[k]));   // the value BN backward will see
-            a0 += dr; a1 = fmaf(dr, q1[k], a1); a2 = fmaf(dr, q2[k], a2); a3 = fmaf(dr, q3[k], a3);
-          }
-        }
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (idx < total && j < npix) body(c, j, a);
         for (int o = vec_per_row >> 1; o > 0; o >>= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-          a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
         }
-        if (idx < total && jv == 0) { accs[c] += a0; accs[C + c] += a1; accs[2 * C + c] += a2; accs[3 * C + c] += a3; }
+        if (idx < total && jv == 0) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) accs[q * C + c] += a[q];
+        }
       }
     } else {
       for (int c = warp; c < C; c += kWarps) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int jv = lane; jv < vec_per_row; jv += 32) {
           const int j = jv * VP;
-          if (j < npix) {
-            const size_t off = ((size_t)n * C + c) * HW + p0 + j;
-            float d[VP], q1[VP], q2[VP], q3[VP];
-#pragma unroll
-            for (int k = 0; k < VP; ++k) d[k] = tile[c * pitch + j + k];
-            st_bf16<VP>(du + off, d);
-            ld_bf16<VP>(y1 + off, q1); ld_bf16<VP>(y2 + off, q2); ld_bf16<VP>(y3 + off, q3);
-#pragma unroll
-            for (int k = 0; k < VP; ++k) {
-              const float dr = __bfloat162float(__float2bfloat16_rn(d[k]));
-              a0 += dr; a1 = fmaf(dr, q1[k], a1); a2 = fmaf(dr, q2[k], a2); a3 = fmaf(dr, q3[k], a3);
-            }
-          }
+          if (j < npix) body(c, j, a);
         }
-        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
-        if (lane == 0) { accs[c] += a0; accs[C + c] += a1; accs[2 * C + c] += a2; accs[3 * C + c] += a3; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a[q] = warp_sum(a[q]);
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) accs[q * C + c] += a[q];
+        }
       }
     }
   }
   __syncthreads();
-  if (regpath) {
-#pragma unroll
-    for (int k = 0; k < KM; ++k) {
-      const int c = 2 * lane + 64 * k;
-      if (c < C) {
-        accw[(warp * 2 + 0) * C + c] = aw0[k]; accw[(warp * 2 + 0) * C + c + 1] = aw1[k];
-        accw[(warp * 2 + 1) * C + c] = ab0[k]; accw[(warp * 2 + 1) * C + c + 1] = ab1[k];
-      }
-    }
-    __syncthreads();
-  }
   float* o = part + (size_t)blockIdx.x * 6 * C;
-  for (int c = tid; c < C; c += kThreads) {
-    float w0 = 0.f, w1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { w0 += accw[(w * 2 + 0) * C + c]; w1 += accw[(w * 2 + 1) * C + c]; }
-    o[c] = w0; o[C + c] = w1;
-    o[2 * C + c] = accs[c]; o[3 * C + c] = accs[C + c]; o[4 * C + c] = accs[2 * C + c]; o[5 * C + c] = accs[3 * C + c];
-  }
+  for (int i = tid; i < 6 * C; i += kThreads) o[i] = accs[i];
 }
 
 // dy_i = A_i*du + B_i*y_i + C_i   (coef: [9][C] = A1..A3, B1..B3, C1..C3)
@@ -724,16 +739,21 @@ int residual_bwd(const float* dout, const void* h2, const float* gamma, const fl
   return SLAK_OK;
 }
 
+static Geo ln_bwd_geo(int N, int C, int HW, size_t* smem) {
+  Geo g = make_geo(N, C, HW, 7, smem);              // u tile + accs [6][C] + lnw [C]
+  *smem += 4 * (size_t)g.PIX * sizeof(float) + (size_t)g.PIX * ln_bwd_gpitch(C) * sizeof(__nv_bfloat16);
+  return g;
+}
 int bn3_sum_ln_bwd_parts(int N, int C, int HW) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, kWarps * 2 + 5, &smem);
+  Geo g = ln_bwd_geo(N, C, HW, &smem);
   return grid_for(g, smem);
 }
 int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
                    const float* shift, const float* lnw, const float* mu, const float* rstd, void* du, float* part,
                    int N, int C, int HW, cudaStream_t st) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, kWarps * 2 + 5, &smem);
+  Geo g = ln_bwd_geo(N, C, HW, &smem);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
   const int vp = pick_vp(HW, y1, y2, y3, du);
   const int grid = grid_for(g, smem);

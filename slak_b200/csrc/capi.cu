@@ -61,6 +61,12 @@ int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* 
 int bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef, void* dy1,
                   void* dy2, void* dy3, int N, int C, int HW, cudaStream_t st);
 }
+// layernorm2d.cu
+int layernorm2d_bwd_parts(int N, int HW);
+int layernorm2d_fwd(const void* x, int xdt, const float* w, const float* b, float eps, void* y, int ydt, float* mean,
+                    float* rstd, int N, int C, int HW, cudaStream_t st);
+int layernorm2d_bwd(const void* g, int gdt, const void* x, int xdt, const float* w, const float* mean, const float* rstd,
+                    void* dx, float* part, float* dw, float* db, int N, int C, int HW, cudaStream_t st);
 // mask.cu
 int mask_apply(float* const* w_ptrs, const float* const* m_ptrs, float* const* e_ptrs,
                const int64_t* numels, int count, int64_t max_numel, cudaStream_t st);
@@ -319,3 +325,22 @@ SLAK_API int slak_mask_prune_magnitude(const float* w, float* mask, int64_t nume
 }
 
 }  // extern "C"
+
+// ---- LayerNorm over channels of NCHW (models/SLaK.py:256-261) -------------------------------------
+SLAK_API int slak_layernorm2d_fwd(const void* x, int x_dtype, const float* w, const float* b, float eps, void* y,
+                                  int y_dtype, float* mean, float* rstd, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(x && w && b && y, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE((mean == nullptr) == (rstd == nullptr), SLAK_ERR_BAD_ARG, "mean and rstd must be given together");
+  SLAK_REQUIRE(N >= 0 && C > 0 && HW >= 0, SLAK_ERR_BAD_ARG, "bad size N=%d C=%d HW=%d", N, C, HW);
+  return layernorm2d_fwd(x, x_dtype, w, b, eps, y, y_dtype, mean, rstd, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_layernorm2d_bwd_parts(int N, int HW) { return layernorm2d_bwd_parts(N, HW); }
+
+SLAK_API int slak_layernorm2d_bwd(const void* g, int g_dtype, const void* x, int x_dtype, const float* w, const float* mean,
+                                  const float* rstd, void* dx, float* part, float* dw, float* db, int N, int C, int HW,
+                                  void* stream) {
+  SLAK_REQUIRE(g && x && w && mean && rstd && dx && part && dw && db, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(N >= 0 && C > 0 && HW >= 0, SLAK_ERR_BAD_ARG, "bad size N=%d C=%d HW=%d", N, C, HW);
+  return layernorm2d_bwd(g, g_dtype, x, x_dtype, w, mean, rstd, dx, part, dw, db, N, C, HW, (cudaStream_t)stream);
+}

@@ -337,10 +337,37 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     float* ex = reinterpret_cast<float*>(sm + Cf::kOffEx);   // [128 rows][64 floats]: band g uses floats [g*T, g*T+T)
     const int PR = W / E;
     constexpr int XM = T / 4 - 1;               // float4-chunk XOR mask inside a band
+    constexpr bool PFB = (E >= 2);              // bf16 addend prefetched into registers (32 per thread)
+    constexpr bool PFF = PFB && (T < 64);       // fp32 addend too (64 more) where the accumulator row is short
     for (int i = 0; i < n_units; ++i) {
       const long long gidx = g0 + i;
       const int c = (int)(gidx / upc), u = (int)(gidx - (long long)c * upc);
       const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
+      // addend rows of this unit are requested BEFORE the accumulators are waited for: one global round trip per
+      // unit, hidden behind the MMAs, instead of one per band and addend after them
+      uint32_t pfb[PFB ? UPS * (T / 2) : 1];
+      uint32_t pff[PFF ? UPS * T : 1];
+      if constexpr (PFB) {
+#pragma unroll
+        for (int g = 0; g < UPS; ++g) {
+          const int n = PLANES * u + g * PPU + pl;
+          if ((n < P.N) && (row < H)) {
+            const size_t rbase = ((size_t)n * P.C + c) * plane_elems + (size_t)row * W;
+#pragma unroll
+            for (int j = 0; j < T / E; ++j)
+              if (j < PR) {
+                if (P.addend) ld_bf16_piece_raw<E>(pfb + g * (T / 2) + j * (E / 2), P.addend + rbase + j * E);
+                if constexpr (PFF) {
+                  if (P.out_f32 && P.addend_f32) ld_f32_piece_raw<E>(pff + g * T + j * E, P.addend_f32 + rbase + j * E);
+                }
+              }
+            if constexpr (!PFF) {       // T = 64: no registers left for the fp32 addend -> at least pull it into L2
+              if (P.out_f32 && P.addend_f32)
+                for (int b = 0; b < W * 4; b += 128) prefetch_l2(reinterpret_cast<const uint8_t*>(P.addend_f32 + rbase) + b);
+            }
+          }
+        }
+      }
       mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
       uint32_t v[T];
@@ -384,9 +411,15 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
           for (int j = 0; j < T / E; ++j)
             if (j < PR) {
-              if (P.addend) add_bf16_piece<E>(v + j * E, P.addend + rbase + j * E);
+              if (P.addend) {
+                if constexpr (PFB) add_bf16_raw<E>(v + j * E, pfb + g * (T / 2) + j * (E / 2));
+                else add_bf16_piece<E>(v + j * E, P.addend + rbase + j * E);
+              }
               if (P.out_f32) {
-                if (P.addend_f32) add_f32_piece<E>(v + j * E, P.addend_f32 + rbase + j * E);
+                if (P.addend_f32) {
+                  if constexpr (PFF) add_f32_raw<E>(v + j * E, pff + g * T + j * E);
+                  else add_f32_piece<E>(v + j * E, P.addend_f32 + rbase + j * E);
+                }
                 store_f32_piece<E>(P.out_f32 + rbase + j * E, v + j * E);
               } else {
                 store_bf16_piece<E>(P.out + rbase + j * E, v + j * E);

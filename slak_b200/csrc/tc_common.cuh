@@ -185,6 +185,44 @@ __device__ __forceinline__ void add_bf16_piece(uint32_t* v, const __nv_bfloat16*
     v[0] = __float_as_uint(__uint_as_float(v[0]) + __bfloat162float(*src));
   }
 }
+// split form of the two adds above: request the piece early (raw registers), add it later
+template <int E>
+__device__ __forceinline__ void ld_bf16_piece_raw(uint32_t* raw, const __nv_bfloat16* src) {   // E/2 registers
+  static_assert(E >= 2, "2-byte pieces are not prefetched");
+  if constexpr (E == 8) { const uint4 t = __ldg(reinterpret_cast<const uint4*>(src)); raw[0] = t.x; raw[1] = t.y; raw[2] = t.z; raw[3] = t.w; }
+  else if constexpr (E == 4) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src)); raw[0] = t.x; raw[1] = t.y; }
+  else { raw[0] = __ldg(reinterpret_cast<const uint32_t*>(src)); }
+}
+template <int E>
+__device__ __forceinline__ void add_bf16_raw(uint32_t* v, const uint32_t* raw) {
+#pragma unroll
+  for (int j = 0; j < E / 2; ++j) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[j]));
+    v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + f.x);
+    v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + f.y);
+  }
+}
+template <int E>
+__device__ __forceinline__ void ld_f32_piece_raw(uint32_t* raw, const float* src) {            // E registers
+  static_assert(E >= 2, "single elements are not prefetched");
+  if constexpr (E >= 4) {
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + k));
+      raw[k] = t.x; raw[k + 1] = t.y; raw[k + 2] = t.z; raw[k + 3] = t.w;
+    }
+  } else {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(src));
+    raw[0] = t.x; raw[1] = t.y;
+  }
+}
+template <int E>
+__device__ __forceinline__ void add_f32_raw(uint32_t* v, const uint32_t* raw) {
+#pragma unroll
+  for (int k = 0; k < E; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(raw[k]));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // fp32 variants: E floats added from / stored to global
 template <int E>
 __device__ __forceinline__ void add_f32_piece(uint32_t* v, const float* src) {

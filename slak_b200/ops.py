@@ -293,3 +293,75 @@ def lk_branches(x, w1, w2, w3):
     if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         raise TypeError("Only support fp32, fp16 and bf16, get {}".format(x.dtype))
     return LKBranchesFunction.apply(x, w1, w2, w3)
+
+
+# ---------------------------------------------------------------------------------------
+# LayerNorm over the channels of an NCHW tensor (models/SLaK.py:256-261, "channels_first")
+# ---------------------------------------------------------------------------------------
+def layernorm2d_forward(x, weight, bias, eps, out_dtype=None, need_stats=True):
+    """y[n,c,h,w] = weight[c] * (x - mean_c) / sqrt(var_c + eps) + bias[c]; returns (y, mean, rstd)."""
+    _check_input(x, "input")
+    if x.dim() != 4 or x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("layernorm2d expects a 4-d fp32 or bf16 NCHW tensor")
+    out_dtype = out_dtype or x.dtype
+    N, C, H, W = x.shape
+    w32 = weight.detach().float().contiguous()
+    b32 = bias.detach().float().contiguous()
+    y = torch.empty((N, C, H, W), dtype=out_dtype, device=x.device)
+    mean = torch.empty(N * H * W, dtype=torch.float32, device=x.device) if need_stats else None
+    rstd = torch.empty_like(mean) if need_stats else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        rc = lib.slak_layernorm2d_fwd(x.data_ptr(), _lib.dtype_code(x.dtype), w32.data_ptr(), b32.data_ptr(), float(eps),
+                                      y.data_ptr(), _lib.dtype_code(out_dtype),
+                                      mean.data_ptr() if need_stats else None, rstd.data_ptr() if need_stats else None,
+                                      N, C, H * W, _lib.current_stream_ptr())
+    _lib.check(rc, "slak_layernorm2d_fwd")
+    _count(1)
+    return y, mean, rstd
+
+
+def layernorm2d_backward(g, x, weight, mean, rstd):
+    """(dx, dweight, dbias) of layernorm2d_forward; dx has x's dtype, the parameter gradients are fp32."""
+    _check_input(g, "grad")
+    _check_input(x, "input")
+    N, C, H, W = x.shape
+    w32 = weight.detach().float().contiguous()
+    lib = _lib.load()
+    parts = lib.slak_layernorm2d_bwd_parts(N, H * W)
+    part = torch.empty(parts * 2 * C, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    dw = torch.empty(C, dtype=torch.float32, device=x.device)
+    db = torch.empty(C, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.slak_layernorm2d_bwd(g.data_ptr(), _lib.dtype_code(g.dtype), x.data_ptr(), _lib.dtype_code(x.dtype),
+                                      w32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), part.data_ptr(),
+                                      dw.data_ptr(), db.data_ptr(), N, C, H * W, _lib.current_stream_ptr())
+    _lib.check(rc, "slak_layernorm2d_bwd")
+    _count(2)
+    return dx, dw, db
+
+
+class LayerNorm2dFunction(torch.autograd.Function):
+    """Autograd node of the channels_first LayerNorm; `out_dtype` lets the caller ask for the dtype its consumer
+    wants (bf16 in front of an autocast conv) instead of a separate cast pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        x = x.contiguous()
+        y, mean, rstd = layernorm2d_forward(x, weight, bias, eps, out_dtype, need_stats=True)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = layernorm2d_backward(g.contiguous(), x, weight, mean, rstd)
+        return dx, dw.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None, None
+
+
+def layernorm2d(x, weight, bias, eps=1e-6, out_dtype=None):
+    if not x.is_cuda:
+        raise RuntimeError("slak_b200.ops.layernorm2d needs CUDA tensors (no CPU fallback)")
+    return LayerNorm2dFunction.apply(x, weight, bias, eps, out_dtype)

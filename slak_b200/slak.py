@@ -188,10 +188,23 @@ class LayerNorm(nn.Module):
         self.eps = eps
         self.data_format = data_format
         self.normalized_shape = (normalized_shape,)
+        self.out_dtype_autocast = None     # set by SLaK for the downsampling layers (see forward)
 
     def forward(self, x):
         if self.data_format == "channels_last":
             return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        if x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16):
+            # one streaming kernel over NCHW (slak_b200/csrc/layernorm2d.cu) instead of ten elementwise/reduce
+            # launches.  Under autocast the reference's expression promotes to fp32 (pow/mean run in fp32), so the
+            # result is fp32 unless the owner of this layer asked for its consumer's dtype (`out_dtype_autocast`:
+            # the stride-2 conv behind a downsampling LayerNorm reads bf16 anyway)
+            out_dtype = torch.float32
+            if torch.is_autocast_enabled():
+                if self.out_dtype_autocast is not None and torch.get_autocast_gpu_dtype() == self.out_dtype_autocast:
+                    out_dtype = self.out_dtype_autocast
+            elif x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16:
+                out_dtype = torch.bfloat16
+            return ops.layernorm2d(x, self.weight, self.bias, self.eps, out_dtype)
         u = x.mean(1, keepdim=True)
         d = x - u
         s = d.pow(2).mean(1, keepdim=True)
@@ -255,6 +268,8 @@ class SLaK(nn.Module):
             self.downsample_layers.append(nn.Sequential(
                 LayerNorm(dims[i], eps=1e-6, data_format="channels_first"),
                 nn.Conv2d(dims[i], dims[i + 1], kernel_size=2, stride=2)))
+            # the conv behind this LayerNorm is autocast-eligible: let the LayerNorm kernel round to bf16 itself
+            self.downsample_layers[-1][0].out_dtype_autocast = torch.bfloat16
 
         rates = [r.item() for r in torch.linspace(0, drop_path_rate, sum(depths))]
         self.stages = nn.ModuleList()
