@@ -302,23 +302,33 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       const int tw = warp - 2;
       const int m = lane >> 3, kk = lane & 7;
       constexpr int NB = T / 8;
+      constexpr int ITERS = 32 / kNumTransposerWarps;
+      // block -> (source, destination) offsets are the same for every unit: computed once
+      uint32_t soff[ITERS], doff[ITERS];
+#pragma unroll
+      for (int q = 0; q < ITERS; ++q) {
+        const int blk = 4 * (tw + q * kNumTransposerWarps) + m;
+        const int g = blk / (2 * T), rem0 = blk - g * (2 * T);
+        const int pl = rem0 / (NB * NB), rem = rem0 - pl * (NB * NB);
+        const int bi = rem / NB, bj = rem - bi * NB;
+        soff[q] = (pl * T + 8 * bi + kk) * 128 + (((g * NB + bj) ^ kk) << 4);
+        doff[q] = (pl * T + 8 * bj + kk) * 128 + (((g * NB + bi) ^ kk) << 4);
+      }
+      const uint32_t xt = base + Cf::kOffXT + kPad;
       for (int i = 0; i < n_units; ++i) {
         const int st = i % kSStages, ph = (i / kSStages) & 1;
         mbar_wait(BAR(B_S_FULL + st), ph);
-        mbar_wait(BAR(B_T_EMPTY), (i & 1) ^ 1);
         const uint32_t xs = base + Cf::kOffXS + st * kUnit;
-        const uint32_t xt = base + Cf::kOffXT + kPad;
-#pragma unroll 4
-        for (int it = tw; it < 32; it += kNumTransposerWarps) {
-          const int blk = 4 * it + m;
-          const int g = blk / (2 * T), rem0 = blk - g * (2 * T);
-          const int pl = rem0 / (NB * NB), rem = rem0 - pl * (NB * NB);
-          const int bi = rem / NB, bj = rem - bi * NB;
-          const uint32_t src = xs + (pl * T + 8 * bi + kk) * 128 + (((g * NB + bj) ^ kk) << 4);
-          const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + (((g * NB + bi) ^ kk) << 4);
-          uint32_t r0, r1, r2, r3;
-          ldmatrix_x4_trans(src, r0, r1, r2, r3);
-          stmatrix_x4(dst, r0, r1, r2, r3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {            // two halves: 8 x4 matrices in registers at a time
+          uint32_t r[ITERS / 2][4];
+#pragma unroll
+          for (int q = 0; q < ITERS / 2; ++q)
+            ldmatrix_x4_trans(xs + soff[h * (ITERS / 2) + q], r[q][0], r[q][1], r[q][2], r[q][3]);
+          if (h == 0) mbar_wait(BAR(B_T_EMPTY), (i & 1) ^ 1);   // the first loads do not depend on the target slot
+#pragma unroll
+          for (int q = 0; q < ITERS / 2; ++q)
+            stmatrix_x4(xt + doff[h * (ITERS / 2) + q], r[q][0], r[q][1], r[q][2], r[q][3]);
         }
         fence_proxy_async();
         __syncwarp();

@@ -22,9 +22,10 @@
 // channels and a builder warp prepares the next channel's Toeplitz set (double-buffered) while the
 // pipeline runs, so short channels do not pay a pipeline drain.
 //
-// Warp roles (352 threads): w0 loader | w1 MMA issuer | w2-3 transposers (w2 owns TMEM alloc) |
-// w4-7 epilogue (TMEM -> registers -> bf16 -> global; y1 is transposed back through smem) |
-// w8-9 extra loaders (cp.async path only) | w10 Toeplitz builder.
+// Warp roles: w0 loader | w1 MMA issuer | w2-3 and w12-13 transposers (w2 owns TMEM alloc) | w4-7 and w8-11 two
+// epilogue warpgroups, one per accumulator buffer, taking alternate units (TMEM -> registers -> bf16 -> global; y1
+// is transposed back through a per-group smem staging tile) | w14-15 extra loaders and w16 Toeplitz builder
+// (cp.async classes only: 544 threads; the TMA class runs 448).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
@@ -36,9 +37,10 @@ constexpr int kStages = 3;                       // X (natural) slots in flight
 constexpr int kAccBufs = 2;
 constexpr int kUnitBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kPad = 1024;                       // zero rows before/after a unit tile
-constexpr int kXSlot = kPad + kUnitBytes + kPad; // 18 KB
-constexpr int kNumTransposerWarps = 2;
-constexpr int kThreads = 352;
+constexpr int kXSlot = kPad + kUnitBytes;        // 17 KB: [zero pad][tile]; the next slot's pad closes this one
+constexpr int kNumTransposerWarps = 4;
+constexpr int kEpiGroups = 2;
+__host__ __device__ constexpr int fwd_threads(bool tma) { return tma ? 448 : 544; }
 
 template <int T> struct FwdCfg {
   static constexpr int PPU = 128 / T;            // row groups per unit
@@ -52,10 +54,13 @@ template <int T> struct FwdCfg {
   static constexpr int kOffToep = 0;
   static constexpr int kOffXN = kOffToep + NT * kToepSet;
   static constexpr int kOffXT = kOffXN + kStages * kXSlot;
-  static constexpr int kOffY1 = kOffXT + kXSlot;
-  static constexpr int kOffW = kOffY1 + kUnitBytes;          // fp32 tap staging of the builder warp (4 KB)
-  static constexpr int kOffBar = kOffW + 4096;
+  static constexpr int kOffY1 = kOffXT + kXSlot + kPad;      // one y1 staging tile per epilogue group
+  // fp32 tap staging (4 KB): the builder warp's own for the multi-channel classes; for T = 64 the one Toeplitz set is
+  // built before the pipeline starts, so the staging aliases the (not yet used) y1 tiles
+  static constexpr int kOffW = (NT == 1) ? kOffY1 : kOffY1 + kEpiGroups * kUnitBytes;
+  static constexpr int kOffBar = kOffY1 + kEpiGroups * kUnitBytes + (NT == 1 ? 0 : 4096);
   static constexpr int kSmem = kOffBar + 1024 + 1024;
+  static_assert(kSmem <= 232448, "shared memory budget");
   static constexpr int kAccCols = 3 * T * UPS;   // 192 for every class
   static constexpr int kTmemCols = 512;
 };
@@ -68,8 +73,9 @@ struct FwdParams {
   int units_per_c;       // ceil(N / PLANES)
   int per_cta;           // work items per CTA; items are (channel, unit) in channel-major order.  For T=64
                          // per_cta divides the channel into `splits` ranges (grid = C * splits)
-  int splits;            // T=64: CTAs per channel; small classes: stats slots per channel
-  float* stats;          // optional [C][splits][6]: per-CTA (sum, sum of squares) of y1, y2, y3 (fp32, before rounding)
+  int splits;            // T=64: CTAs per channel; small classes: CTAs that can touch one channel
+  float* stats;          // optional [C][splits][2][6]: per (CTA, epilogue group) (sum, sum of squares) of y1, y2, y3
+                         // (fp32, before rounding)
 };
 
 // Banded Toeplitz operands of one channel (K-major SWIZZLE_128B): five T1_s tiles at tp, then five [T2_r ; T3_r] tiles.
@@ -113,11 +119,13 @@ __device__ __forceinline__ void build_toeplitz(uint8_t* tp, const float* w1s, co
 }
 
 template <int T, int CB, bool TMA>
-__global__ void __launch_bounds__(kThreads, 1)
-lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
+__global__ void __launch_bounds__(fwd_threads(TMA), 1)
+lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap y1map,
+                  const __grid_constant__ CUtensorMap y2map, const __grid_constant__ CUtensorMap y3map, FwdParams P) {
   using Cfg = FwdCfg<T>;
   constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2, UPS = Cfg::UPS, PLANES = Cfg::PLANES, NT = Cfg::NT;
   constexpr int kNumLoaders = TMA ? 1 : 3;
+  constexpr int kThreads = fwd_threads(TMA);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -162,18 +170,18 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
     mbar_init(BAR(B_XT_EMPTY), 1);                               // MMA commit
     for (int a = 0; a < kAccBufs; ++a) {
       mbar_init(BAR(B_ACC_FULL + a), 1);                         // MMA commit
-      mbar_init(BAR(B_ACC_EMPTY + a), 4);                        // one arrival per epilogue warp
+      mbar_init(BAR(B_ACC_EMPTY + a), 4);                        // one arrival per warp of the group that owns it
     }
     for (int s = 0; s < NT; ++s) {
       mbar_init(BAR(B_TP_FULL + s), 1);                          // builder warp
       mbar_init(BAR(B_TP_EMPTY + s), 1);                         // MMA commit after the channel's last MMA
     }
     mbar_fence_init();
-    if (TMA) tma_prefetch_desc(&xmap);
+    if (TMA) { tma_prefetch_desc(&xmap); tma_prefetch_desc(&y1map); tma_prefetch_desc(&y2map); tma_prefetch_desc(&y3map); }
   }
   {  // X / X^T slots start as zeros: pads and tile padding are never written afterwards
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < (kStages + 1) * kXSlot / 16; i += kThreads)
+    for (int i = tid; i < ((kStages + 1) * kXSlot + kPad) / 16; i += kThreads)
       reinterpret_cast<uint4*>(sm + Cfg::kOffXN)[i] = z;
   }
   if (NT == 1 && n_units > 0) {   // single-channel range: every thread helps building the one Toeplitz set
@@ -195,7 +203,8 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const bool is_loader = (warp == 0) || (!TMA && (warp == 8 || warp == 9));
+  const bool is_loader = (warp == 0) || (!TMA && (warp == 14 || warp == 15));
+  const bool is_transposer = (warp == 2 || warp == 3 || warp == 12 || warp == 13);
   if (is_loader) {
     if constexpr (TMA) {
       // ================= TMA producer (T = 64: two planes per unit) =================
@@ -215,7 +224,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       }
     } else {
       // ================= cp.async loaders: loader j owns slot j (one unit = PLANES planes in flight each) ====
-      const int lj = (warp == 0) ? 0 : (warp - 7);           // 0, 1, 2
+      const int lj = (warp == 0) ? 0 : (warp - 13);          // 0, 1, 2
       PieceMap<CB> pm;
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
@@ -305,29 +314,34 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         umma_commit(BAR(B_ACC_FULL + ab));           // accumulators ready
       }
     }
-  } else if (warp < 4) {
+  } else if (is_transposer) {
     // ================= transposers: X (natural) -> X^T, 8x8 blocks =================
-    const int tw = warp - 2;
+    const int tw = warp < 4 ? warp - 2 : warp - 10;        // 0..3
     const int m = lane >> 3, kk = lane & 7;     // matrix id within the x4, row within the 8x8 block
     constexpr int NB = T / 8;                   // blocks per plane edge
+    constexpr int ITERS = 32 / kNumTransposerWarps;
+    // the block -> (source, destination) offsets are the same for every unit: computed once
+    uint32_t soff[ITERS], doff[ITERS];
+#pragma unroll
+    for (int q = 0; q < ITERS; ++q) {           // 128 8x8 blocks: every T x T block in place
+      const int blk = 4 * (tw + q * kNumTransposerWarps) + m;
+      const int g = blk / (2 * T), rem0 = blk - g * (2 * T);      // column band
+      const int pl = rem0 / (NB * NB), rem = rem0 - pl * (NB * NB);
+      const int bi = rem / NB, bj = rem - bi * NB;
+      soff[q] = (pl * T + 8 * bi + kk) * 128 + (((g * NB + bj) ^ kk) << 4);
+      doff[q] = (pl * T + 8 * bj + kk) * 128 + (((g * NB + bi) ^ kk) << 4);
+    }
+    const uint32_t xt = base + Cfg::kOffXT + kPad;
     for (int i = 0; i < n_units; ++i) {
       const int st = i % kStages, ph = (i / kStages) & 1;
       mbar_wait(BAR(B_XN_FULL + st), ph);       // X landed
-      mbar_wait(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed
       const uint32_t xn = XN_ADDR(st);
-      const uint32_t xt = base + Cfg::kOffXT + kPad;
-#pragma unroll 4
-      for (int it = tw; it < 32; it += kNumTransposerWarps) {       // 128 8x8 blocks: every T x T block in place
-        const int blk = 4 * it + m;
-        const int g = blk / (2 * T), rem0 = blk - g * (2 * T);      // column band
-        const int pl = rem0 / (NB * NB), rem = rem0 - pl * (NB * NB);
-        const int bi = rem / NB, bj = rem - bi * NB;
-        const uint32_t src = xn + (pl * T + 8 * bi + kk) * 128 + (((g * NB + bj) ^ kk) << 4);
-        const uint32_t dst = xt + (pl * T + 8 * bj + kk) * 128 + (((g * NB + bi) ^ kk) << 4);
-        uint32_t r0, r1, r2, r3;
-        ldmatrix_x4_trans(src, r0, r1, r2, r3);
-        stmatrix_x4(dst, r0, r1, r2, r3);
-      }
+      uint32_t r[ITERS][4];
+#pragma unroll
+      for (int q = 0; q < ITERS; ++q) ldmatrix_x4_trans(xn + soff[q], r[q][0], r[q][1], r[q][2], r[q][3]);
+      mbar_wait(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed (the loads above do not depend on it)
+#pragma unroll
+      for (int q = 0; q < ITERS; ++q) stmatrix_x4(xt + doff[q], r[q][0], r[q][1], r[q][2], r[q][3]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
@@ -335,20 +349,25 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         mbar_arrive(BAR(B_XN_EMPTY + st));      // done reading X
       }
     }
-  } else if (warp < 8) {
-    // ================= epilogue =================
-    const int e = warp - 4;
+  } else if (warp < 12) {
+    // ================= epilogue: group wg drains accumulator buffer wg, i.e. units i = wg (mod 2) =================
+    const int wg = (warp - 4) >> 2, e = (warp - 4) & 3;
     const int L = e * 32 + lane;                // TMEM lane = (row group, row)
     const int pl = L / T, row = L % T;
     const size_t plane_elems = (size_t)H * W;
-    uint8_t* y1s = sm + Cfg::kOffY1;
+    uint8_t* y1s = sm + Cfg::kOffY1 + wg * kUnitBytes;
+    const int nb = 1 + wg;                      // named barrier of this group
     const int PR = W / E;                       // pieces per output row
     float st_s[3] = {0.f, 0.f, 0.f}, st_q[3] = {0.f, 0.f, 0.f};   // BatchNorm statistics of this thread's elements
     const bool want_stats = P.stats != nullptr;
     int cur_c = c_first;
     // write the statistics of channel `ch` gathered by this CTA (lanes -> warp -> the four epilogue warps)
     auto flush_stats = [&](int ch) {
-      float* red = reinterpret_cast<float*>(y1s);   // staging is free between units
+      float* red = reinterpret_cast<float*>(y1s);   // staging is free between units (after the TMA class has drained it)
+      if constexpr (TMA) {
+        if (e == 0 && lane == 0) bulk_wait_group_read<0>();
+        named_bar_sync(nb, 128);
+      }
 #pragma unroll
       for (int k2 = 0; k2 < 3; ++k2) {
         float s = st_s[k2], q = st_q[k2];
@@ -357,7 +376,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         if (lane == 0) { red[e * 6 + 2 * k2] = s; red[e * 6 + 2 * k2 + 1] = q; }
         st_s[k2] = 0.f; st_q[k2] = 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(nb, 128);
       // slot: T=64 -> split; multi-channel -> 0 for channels this CTA starts, 1.. when the channel began in an earlier CTA
       int slot = slot0;
       if (T != 64) {
@@ -365,17 +384,83 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
         slot = (int)(blockIdx.x - cta_of_first);
       }
       if (e == 0 && lane < 6 && slot < P.splits)
-        P.stats[((size_t)ch * P.splits + slot) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
-      named_bar_sync(1, 128);
+        P.stats[(((size_t)ch * P.splits + slot) * kEpiGroups + wg) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
+      named_bar_sync(nb, 128);
     };
-    for (int i = 0; i < n_units; ++i) {
+    for (int i = wg; i < n_units; i += kEpiGroups) {
       const long long gidx = g0 + i;
       const int c = (int)(gidx / upc), u = (int)(gidx - (long long)c * upc);
       if (want_stats && c != cur_c) { flush_stats(cur_c); cur_c = c; }
-      const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
+      const int ab = wg, aph = (i / kAccBufs) & 1;
       mbar_wait(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
       uint32_t v[T];
+      if constexpr (TMA) {
+        // T = 64: every output tile goes registers -> swizzled staging tile -> one TMA tile store per plane (the box
+        // is clipped to H x W); row-per-thread global stores would hit 32 different sectors per instruction
+        const int n = PLANES * u + pl;
+        const bool ok = (n < P.N) && (row < H);
+        const uint32_t t0 = tmem + ((uint32_t)(e * 32) << 16) + ab * Cfg::kAccCols;
+        const uint32_t stg = base + Cfg::kOffY1 + wg * kUnitBytes;
+        // the previous tile store of this group must have finished reading the staging tile before it is rewritten;
+        // waiting here (not right after issuing it) lets that read overlap the TMEM load and the statistics
+        auto staging_free = [&]() {
+          if (e == 0 && lane == 0) bulk_wait_group_read<0>();
+          named_bar_sync(nb, 128);
+        };
+        auto store_tile = [&](const CUtensorMap* map) {
+          fence_proxy_async();                      // this thread's staging writes -> visible to the TMA engine
+          named_bar_sync(nb, 128);
+          if (e == 0 && lane == 0) {
+#pragma unroll
+            for (int pq = 0; pq < PPU; ++pq)
+              if (PLANES * u + pq < P.N) tma_store_3d(map, stg + pq * (T * 128), 0, 0, (PLANES * u + pq) * P.C + c);
+            bulk_commit_group();
+          }
+        };
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+          tmem_ld_cols<T>(t0 + T + br * T, v);
+          tmem_ld_wait();
+          if (want_stats && ok) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+              if (j < W) { const float f = __uint_as_float(v[j]); s += f; q = fmaf(f, f, q); }
+            st_s[1 + br] += s; st_q[1 + br] += q;
+          }
+          staging_free();
+#pragma unroll
+          for (int j = 0; j < T / 8; ++j)
+            *reinterpret_cast<uint4*>(y1s + L * 128 + ((j ^ (L & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                           pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                           pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                           pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+          store_tile(br == 0 ? &y2map : &y3map);
+        }
+        tmem_ld_cols<T>(t0, v);                     // y1^T: this thread holds column `row`(=q) for p = 0..T-1
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));   // accumulators drained
+        if (want_stats && n < P.N && row < W) {
+          float s = 0.f, q = 0.f;
+#pragma unroll
+          for (int p = 0; p < T; ++p)
+            if (p < H) { const float f = __uint_as_float(v[p]); s += f; q = fmaf(f, f, q); }
+          st_s[0] += s; st_q[0] += q;
+        }
+        staging_free();
+#pragma unroll
+        for (int p = 0; p < T; ++p) {
+          const uint32_t r = (uint32_t)(pl * T + p);
+          const uint32_t off = r * 128 + ((((uint32_t)row >> 3)) ^ (r & 7)) * 16 + (row & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(v[p]));
+        }
+        store_tile(&y1map);
+        continue;
+      }
 #pragma unroll
       for (int g = 0; g < UPS; ++g) {               // column band g: plane g*PPU + pl
         const int n = PLANES * u + g * PPU + pl;
@@ -421,7 +506,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));   // accumulators drained
-      named_bar_sync(1, 128);
+      named_bar_sync(nb, 128);
 #pragma unroll
       for (int g = 0; g < UPS; ++g) {
         const int n = PLANES * u + g * PPU + pl;
@@ -436,10 +521,13 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams P) {
             }
         }
       }
-      named_bar_sync(1, 128);                     // staging free for the next unit
+      named_bar_sync(nb, 128);                    // staging free for the next unit
     }
     if (want_stats && n_units > 0) flush_stats(cur_c);
-  } else if (warp == 10) {
+    if constexpr (TMA) {
+      if (e == 0 && lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last tile store
+    }
+  } else if (warp == 16) {
     // ================= Toeplitz builder: one set per channel of the range, NT sets in flight =================
     float* w1s = reinterpret_cast<float*>(sm + Cfg::kOffW);   // [KL][5]
     float* w2s = w1s + KL * 5;                                // [5][KL]
@@ -555,17 +643,17 @@ TcPlan tc_plan(int N, int C, int tile, int planes_per_unit) {
 }
 
 template <int T, int CB, bool TMA>
-static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
+static int launch_fwd(const CUtensorMap& map, const CUtensorMap* ymaps, FwdParams& P, cudaStream_t st) {
   using Cfg = FwdCfg<T>;
   const TcPlan plan = tc_plan(P.N, P.C, T, Cfg::PLANES);
   P.units_per_c = plan.units_per_c;
   P.per_cta = plan.per_cta;
   P.splits = plan.splits;
   if (P.stats)   // not every slot of a channel is written in the multi-channel partition
-    SLAK_CUDA_TRY(cudaMemsetAsync(P.stats, 0, (size_t)P.C * plan.splits * 6 * sizeof(float), st));
+    SLAK_CUDA_TRY(cudaMemsetAsync(P.stats, 0, (size_t)P.C * plan.splits * kEpiGroups * 6 * sizeof(float), st));
   auto kern = lk3_fwd_tc_kernel<T, CB, TMA>;
   SLAK_SET_MAX_SMEM(kern, Cfg::kSmem);
-  kern<<<plan.grid, kThreads, Cfg::kSmem, st>>>(map, P);
+  kern<<<plan.grid, fwd_threads(TMA), Cfg::kSmem, st>>>(map, ymaps[0], ymaps[1], ymaps[2], P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
@@ -573,7 +661,7 @@ static int launch_fwd(const CUtensorMap& map, FwdParams& P, cudaStream_t st) {
 int lk3_fwd_tc_splits(int N, int C, int H, int W) {
   const TcShape s = tc_shape(H, W);
   if (s.tile == 0) return 0;
-  return tc_plan(N, C, s.tile, (128 / s.tile) * (64 / s.tile)).splits;
+  return tc_plan(N, C, s.tile, (128 / s.tile) * (64 / s.tile)).splits * kEpiGroups;   // statistics slots per channel
 }
 
 int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3,
@@ -584,9 +672,17 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
   const TcShape s = tc_shape(H, W);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
+  CUtensorMap ymaps[3];
+  memset(ymaps, 0, sizeof(ymaps));
   if (s.tma) {
     int rc = make_plane_map(&map, x, N, C, H, W);
     if (rc) return rc;
+    void* ys[3] = {y1, y2, y3};
+    for (int k = 0; k < 3; ++k) {
+      SLAK_REQUIRE((reinterpret_cast<uintptr_t>(ys[k]) & 15) == 0, SLAK_ERR_BAD_ARG, "outputs must be 16-byte aligned");
+      rc = make_plane_map(&ymaps[k], ys[k], N, C, H, W);
+      if (rc) return rc;
+    }
   }
   FwdParams P;
   P.x = (const __nv_bfloat16*)x;
@@ -594,14 +690,14 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
   P.y1 = (__nv_bfloat16*)y1; P.y2 = (__nv_bfloat16*)y2; P.y3 = (__nv_bfloat16*)y3;
   P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL;
   P.stats = stats;
-  if (s.tile == 64) return launch_fwd<64, 16, true>(map, P, st);
+  if (s.tile == 64) return launch_fwd<64, 16, true>(map, ymaps, P, st);
   if (s.tile == 32) {
-    if (s.cb == 8) return launch_fwd<32, 8, false>(map, P, st);
-    if (s.cb == 4) return launch_fwd<32, 4, false>(map, P, st);
-    return launch_fwd<32, 2, false>(map, P, st);
+    if (s.cb == 8) return launch_fwd<32, 8, false>(map, ymaps, P, st);
+    if (s.cb == 4) return launch_fwd<32, 4, false>(map, ymaps, P, st);
+    return launch_fwd<32, 2, false>(map, ymaps, P, st);
   }
-  if (s.cb == 4) return launch_fwd<16, 4, false>(map, P, st);
-  return launch_fwd<16, 2, false>(map, P, st);
+  if (s.cb == 4) return launch_fwd<16, 4, false>(map, ymaps, P, st);
+  return launch_fwd<16, 2, false>(map, ymaps, P, st);
 }
 
 }  // namespace tc

@@ -278,26 +278,29 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     // ================= transposers: x -> x^T, dy1 -> dy1^T (whole 64 x 64 tiles) ========
     const int tw = warp - 2;
     const int m = lane >> 3, kk = lane & 7;
+    constexpr int ITERS = 32 / kNumTransposerWarps;          // 2 tensors x 64 blocks / 4 per group
+    // block -> (source, destination) offsets inside a stage are the same for every unit: computed once
+    uint32_t soff[ITERS], doff[ITERS];
+#pragma unroll
+    for (int q = 0; q < ITERS; ++q) {
+      const int blk = 4 * (tw + q * kNumTransposerWarps) + m;
+      const int which = blk >> 6, rem = blk & 63;
+      const int bi = rem >> 3, bj = rem & 7;
+      soff[q] = (which ? kOffD1s : kOffXNs) + (8 * bi + kk) * 128 + ((bj ^ kk) << 4);
+      doff[q] = (which ? kOffD1Ts : kOffXTs) + (8 * bj + kk) * 128 + ((bi ^ kk) << 4);
+    }
     for (int i = 0; i < n_units; ++i) {
       const int st = i % kStages, ph = (i / kStages) & 1;
       const int ts = i % kTStages, tph = (i / kTStages) & 1;
       mbar_wait(BAR(B_FULL + st), ph);
-      mbar_wait(BAR(B_TEMPTY + ts), tph ^ 1);
       const uint32_t sb = base + st * kStageBytes;
       const uint32_t tb = base + kOffT + ts * kTStageBytes;
-#pragma unroll 4
-      for (int it = tw; it < 32; it += kNumTransposerWarps) {   // 2 tensors x 64 blocks / 4 per group
-        const int blk = 4 * it + m;
-        const int which = blk >> 6, rem = blk & 63;
-        const int bi = rem >> 3, bj = rem & 7;
-        const uint32_t src0 = sb + (which ? kOffD1s : kOffXNs);
-        const uint32_t dst0 = tb + (which ? kOffD1Ts : kOffXTs);
-        const uint32_t src = src0 + (8 * bi + kk) * 128 + ((bj ^ kk) << 4);
-        const uint32_t dst = dst0 + (8 * bj + kk) * 128 + ((bi ^ kk) << 4);
-        uint32_t r0, r1, r2, r3;
-        ldmatrix_x4_trans(src, r0, r1, r2, r3);
-        stmatrix_x4(dst, r0, r1, r2, r3);
-      }
+      uint32_t r[ITERS][4];
+#pragma unroll
+      for (int q = 0; q < ITERS; ++q) ldmatrix_x4_trans(sb + soff[q], r[q][0], r[q][1], r[q][2], r[q][3]);
+      mbar_wait(BAR(B_TEMPTY + ts), tph ^ 1);              // the loads above do not depend on the target slot
+#pragma unroll
+      for (int q = 0; q < ITERS; ++q) stmatrix_x4(tb + doff[q], r[q][0], r[q][1], r[q][2], r[q][3]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
