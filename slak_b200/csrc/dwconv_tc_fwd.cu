@@ -22,13 +22,23 @@
 // channels and a builder warp prepares the next channel's Toeplitz set (double-buffered) while the
 // pipeline runs, so short channels do not pay a pipeline drain.
 //
-// Warp roles: w0 loader | w1 MMA issuer | w2-3 and w12-13 transposers (w2 owns TMEM alloc) | w4-7 and w8-11 two
-// epilogue warpgroups, one per accumulator buffer, taking alternate units (TMEM -> registers -> bf16 -> global; y1
-// is transposed back through a per-group smem staging tile) | w14-15 extra loaders and w16 Toeplitz builder
-// (cp.async classes only: 544 threads; the TMA class runs 448).
+// Warp roles: w0 loader | w1 MMA issuer | w2-3 transposers (w2 owns TMEM alloc) | w4-7 and w8-11 two epilogue
+// warpgroups, one per accumulator buffer, taking alternate units (TMEM -> registers -> bf16 -> shared staging tile ->
+// global: TMA tile stores in the T = 64 class; y1 is transposed on the way) | w12-13 two more transposers (TMA class,
+// 448 threads) or the two extra cp.async loaders, with w14 the Toeplitz builder (small classes, 480 threads).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
+
+// -DSLAK_ROLE_PROFILE: CTA 0 prints, per warp role, the cycles spent in its main loop and the part of them spent
+// waiting on mbarriers / named barriers (debug aid for finding the critical role; never defined in the product build)
+#ifdef SLAK_ROLE_PROFILE
+#define MBW(bar, par) do { const long long _t0 = clock64(); mbar_wait((bar), (par)); prof_wait += clock64() - _t0; } while (0)
+#define NBS(id, n) do { const long long _t0 = clock64(); named_bar_sync((id), (n)); prof_wait += clock64() - _t0; } while (0)
+#else
+#define MBW(bar, par) mbar_wait((bar), (par))
+#define NBS(id, n) named_bar_sync((id), (n))
+#endif
 
 namespace slak {
 namespace tc {
@@ -38,9 +48,9 @@ constexpr int kAccBufs = 2;
 constexpr int kUnitBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kPad = 1024;                       // zero rows before/after a unit tile
 constexpr int kXSlot = kPad + kUnitBytes;        // 17 KB: [zero pad][tile]; the next slot's pad closes this one
-constexpr int kNumTransposerWarps = 4;
+__host__ __device__ constexpr int fwd_transposers(bool tma) { return tma ? 4 : 2; }
 constexpr int kEpiGroups = 2;
-__host__ __device__ constexpr int fwd_threads(bool tma) { return tma ? 448 : 544; }
+__host__ __device__ constexpr int fwd_threads(bool tma) { return tma ? 448 : 480; }
 
 template <int T> struct FwdCfg {
   static constexpr int PPU = 128 / T;            // row groups per unit
@@ -126,6 +136,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
   constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2, UPS = Cfg::UPS, PLANES = Cfg::PLANES, NT = Cfg::NT;
   constexpr int kNumLoaders = TMA ? 1 : 3;
   constexpr int kThreads = fwd_threads(TMA);
+  constexpr int kNumTransposerWarps = fwd_transposers(TMA);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -202,9 +213,14 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+#ifdef SLAK_ROLE_PROFILE
+  long long prof_wait = 0;
+  const long long prof_t0 = clock64();
+#endif
 
-  const bool is_loader = (warp == 0) || (!TMA && (warp == 14 || warp == 15));
-  const bool is_transposer = (warp == 2 || warp == 3 || warp == 12 || warp == 13);
+  // warps 12-13: two more transposers in the TMA class, the two extra cp.async loaders otherwise
+  const bool is_loader = (warp == 0) || (!TMA && (warp == 12 || warp == 13));
+  const bool is_transposer = (warp == 2 || warp == 3 || (TMA && (warp == 12 || warp == 13)));
   if (is_loader) {
     if constexpr (TMA) {
       // ================= TMA producer (T = 64: two planes per unit) =================
@@ -213,7 +229,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
           const long long g = g0 + i;
           const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
           const int st = i % kStages, ph = (i / kStages) & 1;
-          mbar_wait(BAR(B_XN_EMPTY + st), ph ^ 1);
+          MBW(BAR(B_XN_EMPTY + st), ph ^ 1);
           const int n0 = PLANES * u;
           const uint32_t dst = XN_ADDR(st);
           mbar_expect_tx(BAR(B_XN_FULL + st), kUnitBytes);
@@ -224,7 +240,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
       }
     } else {
       // ================= cp.async loaders: loader j owns slot j (one unit = PLANES planes in flight each) ====
-      const int lj = (warp == 0) ? 0 : (warp - 13);          // 0, 1, 2
+      const int lj = (warp == 0) ? 0 : (warp - 11);          // 0, 1, 2
       PieceMap<CB> pm;
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
@@ -232,7 +248,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         const long long g = g0 + i;
         const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
         const int s = lj, ph = (i / kStages) & 1;             // lj == i % kStages
-        mbar_wait(BAR(B_XN_EMPTY + s), ph ^ 1);
+        MBW(BAR(B_XN_EMPTY + s), ph ^ 1);
         const uint32_t tile = XN_ADDR(s);
         const int n0 = PLANES * u;
         if (CB == 2 && pm.count >= 0 && pm.count <= 2) {
@@ -276,13 +292,13 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         if (c != cur_c) {
           if (k >= 0) umma_commit(BAR(B_TP_EMPTY + (k % NT)));   // previous channel's Toeplitz set is free once its MMAs retire
           cur_c = c; ++k;
-          if (NT > 1) mbar_wait(BAR(B_TP_FULL + (k % NT)), (k / NT) & 1);
+          if (NT > 1) MBW(BAR(B_TP_FULL + (k % NT)), (k / NT) & 1);
         }
         const uint32_t toep = base + Cfg::kOffToep + (k % NT) * Cfg::kToepSet;
         const int st = i % kStages, ph = (i / kStages) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
-        mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);   // epilogue drained this accumulator buffer
-        mbar_wait(BAR(B_XN_FULL + st), ph);          // X landed
+        MBW(BAR(B_ACC_EMPTY + ab), aph ^ 1);   // epilogue drained this accumulator buffer
+        MBW(BAR(B_XN_FULL + st), ph);          // X landed
         tc_fence_after();
         const uint32_t xn = XN_ADDR(st);
         const uint32_t xt = base + Cfg::kOffXT + kPad;
@@ -298,7 +314,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
               umma_bf16(acc + g * 3 * T + T, umma_desc_k_sw128(a, 0), umma_desc_k_sw128(b, 0), idesc23, (r | kk) != 0);
             }
         umma_commit(BAR(B_XN_EMPTY + st));           // X slot free (with the transposers' arrivals)
-        mbar_wait(BAR(B_XT_FULL), i & 1);            // X^T written
+        MBW(BAR(B_XT_FULL), i & 1);            // X^T written
         tc_fence_after();
 #pragma unroll
         for (int g = 0; g < UPS; ++g)
@@ -334,12 +350,12 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     const uint32_t xt = base + Cfg::kOffXT + kPad;
     for (int i = 0; i < n_units; ++i) {
       const int st = i % kStages, ph = (i / kStages) & 1;
-      mbar_wait(BAR(B_XN_FULL + st), ph);       // X landed
+      MBW(BAR(B_XN_FULL + st), ph);       // X landed
       const uint32_t xn = XN_ADDR(st);
       uint32_t r[ITERS][4];
 #pragma unroll
       for (int q = 0; q < ITERS; ++q) ldmatrix_x4_trans(xn + soff[q], r[q][0], r[q][1], r[q][2], r[q][3]);
-      mbar_wait(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed (the loads above do not depend on it)
+      MBW(BAR(B_XT_EMPTY), (i & 1) ^ 1);  // previous X^T consumed (the loads above do not depend on it)
 #pragma unroll
       for (int q = 0; q < ITERS; ++q) stmatrix_x4(xt + doff[q], r[q][0], r[q][1], r[q][2], r[q][3]);
       fence_proxy_async();
@@ -366,7 +382,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
       float* red = reinterpret_cast<float*>(y1s);   // staging is free between units (after the TMA class has drained it)
       if constexpr (TMA) {
         if (e == 0 && lane == 0) bulk_wait_group_read<0>();
-        named_bar_sync(nb, 128);
+        NBS(nb, 128);
       }
 #pragma unroll
       for (int k2 = 0; k2 < 3; ++k2) {
@@ -376,7 +392,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         if (lane == 0) { red[e * 6 + 2 * k2] = s; red[e * 6 + 2 * k2 + 1] = q; }
         st_s[k2] = 0.f; st_q[k2] = 0.f;
       }
-      named_bar_sync(nb, 128);
+      NBS(nb, 128);
       // slot: T=64 -> split; multi-channel -> 0 for channels this CTA starts, 1.. when the channel began in an earlier CTA
       int slot = slot0;
       if (T != 64) {
@@ -385,14 +401,14 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
       }
       if (e == 0 && lane < 6 && slot < P.splits)
         P.stats[(((size_t)ch * P.splits + slot) * kEpiGroups + wg) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
-      named_bar_sync(nb, 128);
+      NBS(nb, 128);
     };
     for (int i = wg; i < n_units; i += kEpiGroups) {
       const long long gidx = g0 + i;
       const int c = (int)(gidx / upc), u = (int)(gidx - (long long)c * upc);
       if (want_stats && c != cur_c) { flush_stats(cur_c); cur_c = c; }
       const int ab = wg, aph = (i / kAccBufs) & 1;
-      mbar_wait(BAR(B_ACC_FULL + ab), aph);
+      MBW(BAR(B_ACC_FULL + ab), aph);
       tc_fence_after();
       uint32_t v[T];
       if constexpr (TMA) {
@@ -406,11 +422,11 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         // waiting here (not right after issuing it) lets that read overlap the TMEM load and the statistics
         auto staging_free = [&]() {
           if (e == 0 && lane == 0) bulk_wait_group_read<0>();
-          named_bar_sync(nb, 128);
+          NBS(nb, 128);
         };
         auto store_tile = [&](const CUtensorMap* map) {
           fence_proxy_async();                      // this thread's staging writes -> visible to the TMA engine
-          named_bar_sync(nb, 128);
+          NBS(nb, 128);
           if (e == 0 && lane == 0) {
 #pragma unroll
             for (int pq = 0; pq < PPU; ++pq)
@@ -418,46 +434,56 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             bulk_commit_group();
           }
         };
-#pragma unroll
-        for (int br = 0; br < 2; ++br) {
-          tmem_ld_cols<T>(t0 + T + br * T, v);
-          tmem_ld_wait();
+        uint32_t* va = v;
+        uint32_t* vb = v + 32;
+        auto chunk_nat = [&](int br, int h, const uint32_t* w) {      // columns 32h .. 32h+31 of y2 / y3, row L
           if (want_stats && ok) {
             float s = 0.f, q = 0.f;
 #pragma unroll
-            for (int j = 0; j < T; ++j)
-              if (j < W) { const float f = __uint_as_float(v[j]); s += f; q = fmaf(f, f, q); }
+            for (int j = 0; j < 32; ++j)
+              if (32 * h + j < W) { const float f = __uint_as_float(w[j]); s += f; q = fmaf(f, f, q); }
             st_s[1 + br] += s; st_q[1 + br] += q;
           }
-          staging_free();
 #pragma unroll
-          for (int j = 0; j < T / 8; ++j)
-            *reinterpret_cast<uint4*>(y1s + L * 128 + ((j ^ (L & 7)) << 4)) =
-                make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                           pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                           pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                           pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-          store_tile(br == 0 ? &y2map : &y3map);
-        }
-        tmem_ld_cols<T>(t0, v);                     // y1^T: this thread holds column `row`(=q) for p = 0..T-1
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(y1s + L * 128 + (((4 * h + j) ^ (L & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(w[8 * j]), __uint_as_float(w[8 * j + 1])),
+                           pack_bf16(__uint_as_float(w[8 * j + 2]), __uint_as_float(w[8 * j + 3])),
+                           pack_bf16(__uint_as_float(w[8 * j + 4]), __uint_as_float(w[8 * j + 5])),
+                           pack_bf16(__uint_as_float(w[8 * j + 6]), __uint_as_float(w[8 * j + 7])));
+        };
+        auto chunk_t = [&](int h, const uint32_t* w) {                // y1^T: column q = row, p = 32h .. 32h+31
+          if (want_stats && n < P.N && row < W) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int p = 0; p < 32; ++p)
+              if (32 * h + p < H) { const float f = __uint_as_float(w[p]); s += f; q = fmaf(f, f, q); }
+            st_s[0] += s; st_q[0] += q;
+          }
+#pragma unroll
+          for (int p = 0; p < 32; ++p) {
+            const uint32_t r = (uint32_t)(pl * T + 32 * h + p);
+            const uint32_t off = r * 128 + ((((uint32_t)row >> 3)) ^ (r & 7)) * 16 + (row & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(w[p]));
+          }
+        };
+        tmem_ld32(t0 + T, va); tmem_ld32(t0 + T + 32, vb);
+        tmem_ld_wait();
+        staging_free();
+        chunk_nat(0, 0, va); chunk_nat(0, 1, vb);
+        store_tile(&y2map);
+        tmem_ld32(t0 + 2 * T, va); tmem_ld32(t0 + 2 * T + 32, vb);
+        tmem_ld_wait();
+        staging_free();
+        chunk_nat(1, 0, va); chunk_nat(1, 1, vb);
+        store_tile(&y3map);
+        tmem_ld32(t0, va); tmem_ld32(t0 + 32, vb);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));   // accumulators drained
-        if (want_stats && n < P.N && row < W) {
-          float s = 0.f, q = 0.f;
-#pragma unroll
-          for (int p = 0; p < T; ++p)
-            if (p < H) { const float f = __uint_as_float(v[p]); s += f; q = fmaf(f, f, q); }
-          st_s[0] += s; st_q[0] += q;
-        }
         staging_free();
-#pragma unroll
-        for (int p = 0; p < T; ++p) {
-          const uint32_t r = (uint32_t)(pl * T + p);
-          const uint32_t off = r * 128 + ((((uint32_t)row >> 3)) ^ (r & 7)) * 16 + (row & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(y1s + off) = __float2bfloat16_rn(__uint_as_float(v[p]));
-        }
+        chunk_t(0, va); chunk_t(1, vb);
         store_tile(&y1map);
         continue;
       }
@@ -506,7 +532,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));   // accumulators drained
-      named_bar_sync(nb, 128);
+      NBS(nb, 128);
 #pragma unroll
       for (int g = 0; g < UPS; ++g) {
         const int n = PLANES * u + g * PPU + pl;
@@ -521,20 +547,20 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             }
         }
       }
-      named_bar_sync(nb, 128);                    // staging free for the next unit
+      NBS(nb, 128);                    // staging free for the next unit
     }
     if (want_stats && n_units > 0) flush_stats(cur_c);
     if constexpr (TMA) {
       if (e == 0 && lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last tile store
     }
-  } else if (warp == 16) {
+  } else if (warp == 14) {
     // ================= Toeplitz builder: one set per channel of the range, NT sets in flight =================
     float* w1s = reinterpret_cast<float*>(sm + Cfg::kOffW);   // [KL][5]
     float* w2s = w1s + KL * 5;                                // [5][KL]
     float* w3s = w2s + KL * 5;                                // [5][5]
     for (int c = (NT == 1 ? c_last + 1 : c_first), k = 0; c <= c_last; ++c, ++k) {   // NT == 1: built by all threads below
       const int set = k % NT;
-      mbar_wait(BAR(B_TP_EMPTY + set), ((k / NT) & 1) ^ 1);
+      MBW(BAR(B_TP_EMPTY + set), ((k / NT) & 1) ^ 1);
       uint8_t* tp = sm + Cfg::kOffToep + set * Cfg::kToepSet;
       for (int i = lane; i < KL * 5; i += 32) {
         w1s[i] = P.w1[(size_t)c * KL * 5 + i];
@@ -549,6 +575,10 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     }
   }
 
+#ifdef SLAK_ROLE_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("T=%d warp %2d: loop %lld cycles, waiting %lld, units %d\n", T, warp, clock64() - prof_t0, prof_wait, n_units);
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem);
