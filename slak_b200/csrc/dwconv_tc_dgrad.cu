@@ -30,7 +30,11 @@ constexpr int kUnit = 128 * 128;
 constexpr int kPad = 1024;
 constexpr int kSlot = kPad + kUnit + kPad;     // 18 KB
 constexpr int kNumTransposerWarps = 2;
-constexpr int kThreads = 352;
+// cp.async classes: loader warps per natural-path slot.  A second warp per slot (w11-13 next to w0, w8-9, as the
+// forward and weight-gradient kernels do for the 16-class) is wired up but not enabled: the 448-thread CTA caps the
+// epilogue at 128 registers and its prefetched addend rows spill (measured 165 -> 222 us at 14x14)
+__host__ __device__ constexpr int loader_split(int T) { (void)T; return 1; }
+__host__ __device__ constexpr int threads(int T) { return loader_split(T) == 2 ? 448 : 352; }
 template <int T> struct Cfg {
   static constexpr int PPU = 128 / T;
   static constexpr int UPS = 64 / T;
@@ -102,11 +106,13 @@ __device__ __forceinline__ void stage_taps(const DgradParams& P, int c, float* w
 }
 
 template <int T, int CB, bool TMA>
-__global__ void __launch_bounds__(dg::kThreads, 1)
+__global__ void __launch_bounds__(dg::threads(T), 1)
 lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap nmap, DgradParams P) {
   using namespace dg;
   using Cf = Cfg<T>;
   constexpr int PPU = Cf::PPU, UPS = Cf::UPS, PLANES = Cf::PLANES, KSTEPS = Cf::KSTEPS, NT = Cf::NT, E = CB / 2;
+  constexpr int kThreads = threads(T);
+  constexpr int kSplit = loader_split(T);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -139,8 +145,8 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Cf::kOffBar + 768);
 
   if (tid == 0) {
-    for (int s = 0; s < kNStages; ++s) { mbar_init(BAR(B_N_FULL + s), 1); mbar_init(BAR(B_N_EMPTY + s), 1); }
-    for (int s = 0; s < kSStages; ++s) { mbar_init(BAR(B_S_FULL + s), 1); mbar_init(BAR(B_S_EMPTY + s), kNumTransposerWarps); }
+    for (int s = 0; s < kNStages; ++s) { mbar_init(BAR(B_N_FULL + s), TMA ? 1 : kSplit); mbar_init(BAR(B_N_EMPTY + s), 1); }
+    for (int s = 0; s < kSStages; ++s) { mbar_init(BAR(B_S_FULL + s), TMA ? 1 : kSplit); mbar_init(BAR(B_S_EMPTY + s), kNumTransposerWarps); }
     mbar_init(BAR(B_T_FULL), kNumTransposerWarps);
     mbar_init(BAR(B_T_EMPTY), 1);
     for (int a = 0; a < kAccBufs; ++a) { mbar_init(BAR(B_ACC_FULL + a), 1); mbar_init(BAR(B_ACC_EMPTY + a), 4); }
@@ -166,7 +172,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const bool is_loader = (warp == 0) || (!TMA && (warp == 8 || warp == 9));
+  const bool is_loader = (warp == 0) || (!TMA && (warp == 8 || warp == 9 || warp >= 11));   // w11+: only with a split
   if (is_loader) {
     if constexpr (TMA) {
       if (elect_one()) {
@@ -196,7 +202,10 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     } else {
       // three cp.async loader warps; loader j owns natural slot j; the source slots alternate per unit
-      const int lj = (warp == 0) ? 0 : (warp - 7);
+      const int lj = (warp == 0) ? 0 : (warp < 11 ? warp - 7 : warp - 11);   // natural slot 0..2
+      const int hf = warp >= 11 ? 1 : 0;
+      constexpr int QN = PLANES / kSplit;
+      const int qlo = hf * QN, qhi = qlo + QN;
       PieceMap<CB> pm;
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
@@ -211,14 +220,14 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t tn = base + Cf::kOffXN + st * kSlot + kPad;
         const uint32_t ts = base + Cf::kOffXS + ss * kUnit;
         if (CB == 2 && pm.count >= 0 && pm.count <= 2) {
-          for (int q0 = 0; q0 < PLANES; q0 += 8) {
+          for (int q0 = qlo; q0 < qhi; q0 += 8) {
             const uint8_t* sn[8]; const uint8_t* stt[8]; int r0s[8], c0s[8];
             int cnt = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int q = q0 + j;
               sn[j] = reinterpret_cast<const uint8_t*>(P.in_n); stt[j] = sn[j]; r0s[j] = 0; c0s[j] = 0;
-              if (q < PLANES && n0 + q < P.N) {
+              if (q < qhi && n0 + q < P.N) {
                 const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
                 sn[j] = reinterpret_cast<const uint8_t*>(P.in_n) + off;
                 stt[j] = has_t ? reinterpret_cast<const uint8_t*>(P.in_t) + off : sn[j];
@@ -232,7 +241,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             }
           }
         } else {
-          for (int q = 0; q < PLANES; ++q)
+          for (int q = qlo; q < qhi; ++q)
             if (n0 + q < P.N) {
               const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
               load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.in_n) + off, tn, (q % PPU) * T, (q / PPU) * (T / 8), lane);
@@ -469,7 +478,7 @@ static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParam
   P.splits = plan.splits;
   auto kern = lk_dgrad_tc_kernel<T, CB, TMA>;
   SLAK_SET_MAX_SMEM(kern, Cf::kSmem);
-  kern<<<plan.grid, dg::kThreads, Cf::kSmem, st>>>(mt, mn, P);
+  kern<<<plan.grid, dg::threads(T), Cf::kSmem, st>>>(mt, mn, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }

@@ -25,7 +25,8 @@
 // Warp roles: w0 loader | w1 MMA issuer | w2-3 transposers (w2 owns TMEM alloc) | w4-7 and w8-11 two epilogue
 // warpgroups, one per accumulator buffer, taking alternate units (TMEM -> registers -> bf16 -> shared staging tile ->
 // global: TMA tile stores in the T = 64 class; y1 is transposed on the way) | w12-13 two more transposers (TMA class,
-// 448 threads) or the two extra cp.async loaders, with w14 the Toeplitz builder (small classes, 480 threads).
+// 448 threads) or cp.async loaders, with w14 the Toeplitz builder and w15-17 three more loaders (small classes, 576
+// threads: every X slot is filled by two warps, 4-byte cp.async is bound by per-warp latency).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
@@ -50,7 +51,11 @@ constexpr int kPad = 1024;                       // zero rows before/after a uni
 constexpr int kXSlot = kPad + kUnitBytes;        // 17 KB: [zero pad][tile]; the next slot's pad closes this one
 __host__ __device__ constexpr int fwd_transposers(bool tma) { return tma ? 4 : 2; }
 constexpr int kEpiGroups = 2;
-__host__ __device__ constexpr int fwd_threads(bool tma) { return tma ? 448 : 480; }
+// cp.async classes: loader warps per X slot (each takes a share of the planes).  4-byte cp.async is bound by per-warp
+// latency, so the 16-class (32 planes of <= 392 B per unit) runs two warps per slot; for the 32-class the extra warps
+// cost more (register cap of a 576-thread CTA) than they bring
+__host__ __device__ constexpr int fwd_loader_split(int T) { return T == 16 ? 2 : 1; }
+__host__ __device__ constexpr int fwd_threads(int T, bool tma) { return tma ? 448 : (T == 16 ? 576 : 480); }
 
 template <int T> struct FwdCfg {
   static constexpr int PPU = 128 / T;            // row groups per unit
@@ -129,13 +134,14 @@ __device__ __forceinline__ void build_toeplitz(uint8_t* tp, const float* w1s, co
 }
 
 template <int T, int CB, bool TMA>
-__global__ void __launch_bounds__(fwd_threads(TMA), 1)
+__global__ void __launch_bounds__(fwd_threads(T, TMA), 1)
 lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap y1map,
                   const __grid_constant__ CUtensorMap y2map, const __grid_constant__ CUtensorMap y3map, FwdParams P) {
   using Cfg = FwdCfg<T>;
   constexpr int PPU = Cfg::PPU, KSTEPS = Cfg::KSTEPS, E = CB / 2, UPS = Cfg::UPS, PLANES = Cfg::PLANES, NT = Cfg::NT;
   constexpr int kNumLoaders = TMA ? 1 : 3;
-  constexpr int kThreads = fwd_threads(TMA);
+  constexpr int kThreads = fwd_threads(T, TMA);
+  constexpr int kLoaderSplit = fwd_loader_split(T);
   constexpr int kNumTransposerWarps = fwd_transposers(TMA);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -174,7 +180,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(BAR(B_XN_FULL + s), 1);                          // TMA expect_tx arrive / loader lane 0
+      mbar_init(BAR(B_XN_FULL + s), TMA ? 1 : kLoaderSplit);     // TMA expect_tx arrive / lane 0 of each loader warp of the slot
       mbar_init(BAR(B_XN_EMPTY + s), 1 + kNumTransposerWarps);   // MMA commit + transposers done reading
     }
     mbar_init(BAR(B_XT_FULL), kNumTransposerWarps);              // transposers wrote X^T
@@ -219,7 +225,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
 #endif
 
   // warps 12-13: two more transposers in the TMA class, the two extra cp.async loaders otherwise
-  const bool is_loader = (warp == 0) || (!TMA && (warp == 12 || warp == 13));
+  const bool is_loader = (warp == 0) || (!TMA && (warp == 12 || warp == 13 || warp >= 15));   // w15+: only with a split
   const bool is_transposer = (warp == 2 || warp == 3 || (TMA && (warp == 12 || warp == 13)));
   if (is_loader) {
     if constexpr (TMA) {
@@ -240,7 +246,11 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
       }
     } else {
       // ================= cp.async loaders: loader j owns slot j (one unit = PLANES planes in flight each) ====
-      const int lj = (warp == 0) ? 0 : (warp - 11);          // 0, 1, 2
+      // slot lj = 0, 1, 2 is filled by two warps: (w0, w15), (w12, w16), (w13, w17); each takes half of the planes
+      const int lj = (warp == 0) ? 0 : (warp < 15 ? warp - 11 : warp - 15);
+      const int hf = warp >= 15 ? 1 : 0;
+      constexpr int QN = PLANES / kLoaderSplit;
+      const int qlo = hf * QN, qhi = qlo + QN;
       PieceMap<CB> pm;
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
@@ -253,14 +263,14 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         const int n0 = PLANES * u;
         if (CB == 2 && pm.count >= 0 && pm.count <= 2) {
           // batches of 8 planes: loads first, then stores
-          for (int q0 = 0; q0 < PLANES; q0 += 8) {
+          for (int q0 = qlo; q0 < qhi; q0 += 8) {
             const uint8_t* srcs[8]; int r0s[8], c0s[8];
             int cnt = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int q = q0 + j;
               srcs[j] = reinterpret_cast<const uint8_t*>(P.x); r0s[j] = 0; c0s[j] = 0;
-              if (q < PLANES && n0 + q < P.N) {
+              if (q < qhi && n0 + q < P.N) {
                 srcs[j] = reinterpret_cast<const uint8_t*>(P.x) + ((size_t)(n0 + q) * P.C + c) * plane_bytes;
                 r0s[j] = (q % PPU) * T; c0s[j] = (q / PPU) * (T / 8);
                 cnt = j + 1;
@@ -269,7 +279,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             if constexpr (CB == 2) load_plane_blocks_cb2<8>(pm, srcs, tile, r0s, c0s, cnt, lane);
           }
         } else {
-          for (int q = 0; q < PLANES; ++q)
+          for (int q = qlo; q < qhi; ++q)
             if (n0 + q < P.N)
               load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.x) + ((size_t)(n0 + q) * P.C + c) * plane_bytes,
                                    tile, (q % PPU) * T, (q / PPU) * (T / 8), lane);
@@ -683,7 +693,7 @@ static int launch_fwd(const CUtensorMap& map, const CUtensorMap* ymaps, FwdParam
     SLAK_CUDA_TRY(cudaMemsetAsync(P.stats, 0, (size_t)P.C * plan.splits * kEpiGroups * 6 * sizeof(float), st));
   auto kern = lk3_fwd_tc_kernel<T, CB, TMA>;
   SLAK_SET_MAX_SMEM(kern, Cfg::kSmem);
-  kern<<<plan.grid, fwd_threads(TMA), Cfg::kSmem, st>>>(map, ymaps[0], ymaps[1], ymaps[2], P);
+  kern<<<plan.grid, fwd_threads(T, TMA), Cfg::kSmem, st>>>(map, ymaps[0], ymaps[1], ymaps[2], P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }

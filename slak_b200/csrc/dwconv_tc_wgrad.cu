@@ -55,7 +55,10 @@ constexpr int kOffScr = kOffT + kTStages * kTStageBytes;
 constexpr int kOffBar = kOffScr + ((128 * kScratchPitch * 4 + 1023) / 1024) * 1024;
 constexpr int kSmemBytes = kOffBar + 1024 + 1024;
 constexpr int kNumTransposerWarps = 4;
-constexpr int kThreads = 416;
+// cp.async classes: loader warps per stage.  4-byte cp.async is bound by per-warp latency, so the 16-class (16 planes
+// x 4 tensors per unit) runs two warps per stage, each taking half of the planes (w13-16 join w0, w10-12)
+__host__ __device__ constexpr int loader_split(int T) { return T == 16 ? 2 : 1; }
+__host__ __device__ constexpr int threads(int T) { return T == 16 ? 544 : 416; }
 }  // namespace wg
 
 struct WgradParams {
@@ -89,13 +92,15 @@ __device__ __forceinline__ void zero_plane_block(uint8_t* tile, int row0, int cb
 }
 
 template <int T, int CB, bool TMA>
-__global__ void __launch_bounds__(wg::kThreads, 1)
+__global__ void __launch_bounds__(wg::threads(T), 1)
 lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap d1map,
                     const __grid_constant__ CUtensorMap d2map, const __grid_constant__ CUtensorMap d3map,
                     WgradParams P) {
   using namespace wg;
   constexpr int PPT = 64 / T;                  // plane blocks per tile edge
   constexpr int PLANES = PPT * PPT;            // planes per unit (1, 4, 16)
+  constexpr int kThreads = threads(T);
+  constexpr int kSplit = loader_split(T);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -125,7 +130,7 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(BAR(B_FULL + s), 1);
+      mbar_init(BAR(B_FULL + s), TMA ? 1 : kSplit);
       mbar_init(BAR(B_EMPTY + s), 1 + kNumTransposerWarps);
     }
     for (int s = 0; s < kTStages; ++s) {
@@ -148,7 +153,7 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const bool is_loader = (warp == 0) || (!TMA && warp >= 10);
+  const bool is_loader = (warp == 0) || (!TMA && warp >= 10);     // w13+: second warp of a stage (16-class only)
   if (is_loader) {
     if constexpr (TMA) {
       if (elect_one()) {
@@ -168,7 +173,10 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       }
     } else {
       // four cp.async loader warps, loader j owns stage j
-      const int lj = (warp == 0) ? 0 : (warp - 9);           // 0..3
+      const int lj = (warp == 0) ? 0 : (warp < 13 ? warp - 9 : warp - 13);   // stage 0..3
+      const int hf = warp >= 13 ? 1 : 0;
+      constexpr int QN = PLANES / kSplit;
+      const int qlo = hf * QN, qhi = qlo + QN;
       PieceMap<CB> pm;
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
@@ -180,7 +188,7 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const uint32_t sb = base + st * kStageBytes;
         uint8_t* sbp = sm + st * kStageBytes;
         const int n0 = PLANES * u;
-        for (int q0 = 0; q0 < PLANES; q0 += 4) {
+        for (int q0 = qlo; q0 < qhi; q0 += 4) {
           if (CB == 2 && pm.count >= 0 && pm.count <= 2) {
             const uint8_t* sx[4]; const uint8_t* s1[4]; const uint8_t* s2[4]; const uint8_t* s3[4]; int r0s[4], c0s[4];
             int cnt = 0;
@@ -188,7 +196,7 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             for (int j = 0; j < 4; ++j) {
               const int q = q0 + j;
               sx[j] = s1[j] = s2[j] = s3[j] = reinterpret_cast<const uint8_t*>(P.x); r0s[j] = 0; c0s[j] = 0;
-              if (q < PLANES && n0 + q < P.N) {
+              if (q < qhi && n0 + q < P.N) {
                 const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
                 sx[j] = reinterpret_cast<const uint8_t*>(P.x) + off; s1[j] = reinterpret_cast<const uint8_t*>(P.dy1) + off;
                 s2[j] = reinterpret_cast<const uint8_t*>(P.dy2) + off; s3[j] = reinterpret_cast<const uint8_t*>(P.dy3) + off;
@@ -203,7 +211,7 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
               load_plane_blocks_cb2<4>(pm, s1, sb + kOffD1s, r0s, c0s, cnt, lane);
             }
           } else {
-            for (int q = q0; q < q0 + 4 && q < PLANES; ++q)
+            for (int q = q0; q < q0 + 4 && q < qhi; ++q)
               if (n0 + q < P.N) {
                 const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
                 const int r0 = (q % PPT) * T, c0 = (q / PPT) * (T / 8);
@@ -215,7 +223,7 @@ lk3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           }
         }
         if (n0 + PLANES > P.N)                               // tail: planes that do not exist must read as zero gradients
-          for (int q = 0; q < PLANES; ++q)
+          for (int q = qlo; q < qhi; ++q)
             if (n0 + q >= P.N) {
               const int r0 = (q % PPT) * T, c0 = (q / PPT) * (T / 8);
               zero_plane_block<T>(sbp + kOffD2s, r0, c0, lane);
@@ -411,7 +419,7 @@ template <int T, int CB, bool TMA>
 static int launch_wgrad(const CUtensorMap* maps, WgradParams& P, int grid, cudaStream_t st) {
   auto kern = lk3_wgrad_tc_kernel<T, CB, TMA>;
   SLAK_SET_MAX_SMEM(kern, wg::kSmemBytes);
-  kern<<<grid, wg::kThreads, wg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  kern<<<grid, wg::threads(T), wg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
