@@ -177,6 +177,11 @@ SLAK_API int slak_bn3_finalize_bwd(const float* S, double count, const float* co
 SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef,
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
 
+/* out[c] = sum over r of part[r*cols + c], rows added in a fixed order: folds the per-CTA partial rows the
+ * *_parts kernels above emit (bias / gamma / LayerNorm-parameter gradients: the column sums the reference gets
+ * from autograd's `grad.sum(0)` of nn.Linear / the `gamma * x` broadcast, models/SLaK.py:158-164). */
+SLAK_API int slak_colsum_f32(const float* part, int rows, int cols, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------
  * LayerNorm over the channels of an NCHW tensor: the "channels_first" branch of
  * LayerNorm.forward (models/SLaK.py:256-261), used by the stem and the three

@@ -36,6 +36,15 @@ def _ck(rc, what):
     _lib.check(rc, what)
 
 
+def _colsum(lib, part2d, st):
+    """Fixed-order sum over the per-CTA partial rows [rows, cols] -> [cols] (one small launch of this library)."""
+    rows, cols = part2d.shape
+    out = torch.empty(cols, dtype=torch.float32, device=part2d.device)
+    _ck(lib.slak_colsum_f32(_p(part2d), rows, cols, _p(out), st), "slak_colsum_f32")
+    ops._count(1)
+    return out
+
+
 def _dist_world():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -140,7 +149,7 @@ class FusedBlockFunction(torch.autograd.Function):
         dgp = torch.empty((parts, 2, C), dtype=torch.float32, device=dev)
         _ck(lib.slak_block_residual_bwd(_p(dout), _p(h2), _p(gamma), _p(dp), _p(dh2), _p(dgp), N, C, HW, st),
             "slak_block_residual_bwd")
-        dg2 = dgp.sum(0)
+        dg2 = _colsum(lib, dgp.view(parts, 2 * C), st).view(2, C)
         dgamma, db2 = dg2[0], dg2[1]
         # ---- MLP backward (cuBLAS GEMMs + one fused GELU'/bias-gradient pass) -----------------------------
         dW2 = torch.mm(dh2.t(), a).float()
@@ -150,7 +159,7 @@ class FusedBlockFunction(torch.autograd.Function):
         hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
         _ck(lib.slak_gelu_bwd_bias(_p(da), _p(h), _p(da), _p(hp), N * HW, K, st), "slak_gelu_bwd_bias")   # in place
         dh = da
-        db1 = hp.sum(0)
+        db1 = _colsum(lib, hp, st)
         xf = xn.view(N * HW, C)
         dW1 = torch.mm(dh.t(), xf).float()
         dxn = torch.mm(dh, W1b)
@@ -161,7 +170,7 @@ class FusedBlockFunction(torch.autograd.Function):
         part = torch.empty((parts, 6, C), dtype=torch.float32, device=dev)
         _ck(lib.slak_bn3_sum_ln_bwd(_p(dxn), _p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(mu), _p(rstd),
                                     _p(du), _p(part), N, C, HW, st), "slak_bn3_sum_ln_bwd")
-        red = part.sum(0)                        # [6][C]
+        red = _colsum(lib, part.view(parts, 6 * C), st).view(6, C)
         dlnw, dlnb = red[0], red[1]
         S = red[2:6].contiguous()
         if cfg["sync_bn"]:

@@ -80,14 +80,24 @@ bn3_sum_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y1, const __nv_bfloat16*
                       const float* __restrict__ shift /*[C]*/, const float* __restrict__ lnw,
                       const float* __restrict__ lnb, float eps, __nv_bfloat16* __restrict__ xn,
                       float* __restrict__ mu, float* __restrict__ rstd, Geo g) {
-  extern __shared__ float tile[];   // [C][pitch]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ float tile[];   // [C][pitch] | lnw [C] | lnb [C] | ps, pq [kThreads] | mean, rstd [PIX]
+  const int tid = threadIdx.x;
   const int C = g.C, HW = g.HW, PIX = g.PIX, pitch = g.pitch;
   const int vec_per_row = PIX / VP;
+  float* lnw_s = tile + (size_t)C * pitch;
+  float* lnb_s = lnw_s + C;
+  float* ps = lnb_s + C;
+  float* pq = ps + kThreads;
+  float* mean_s = pq + kThreads;
+  float* rstd_s = mean_s + PIX;
+  for (int i = tid; i < C; i += kThreads) { lnw_s[i] = lnw[i]; lnb_s[i] = lnb[i]; }
+  const int nparts = kThreads / PIX;          // threads per pixel in the statistics pass (PIX <= 128)
+  const int pj = tid % PIX, part = tid / PIX;
   for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
     const int n = t / g.tiles_per_img, p0 = (t - n * g.tiles_per_img) * PIX;
     const int npix = min(PIX, HW - p0);
     __syncthreads();
+    // phase 1: u = sum_i scale_i*y_i + shift, NCHW rows -> tile
     for (int idx = tid; idx < C * vec_per_row; idx += kThreads) {
       const int c = idx / vec_per_row, jv = idx - c * vec_per_row;
       const int j = jv * VP;
@@ -101,24 +111,41 @@ bn3_sum_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y1, const __nv_bfloat16*
       }
     }
     __syncthreads();
-    for (int j = warp; j < npix; j += kWarps) {
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += tile[c * pitch + j];
-      const float mean = warp_sum(s) / C;
-      float q = 0.f;
-      for (int c = lane; c < C; c += 32) { const float d = tile[c * pitch + j] - mean; q = fmaf(d, d, q); }
-      const float r = rsqrtf(warp_sum(q) / C + eps);
-      const size_t pix = (size_t)n * HW + p0 + j;
-      if (lane == 0) { mu[pix] = mean; rstd[pix] = r; }
-      __nv_bfloat16* o = xn + pix * C;
-      if ((C & 1) == 0) {
-        for (int c = 2 * lane; c < C; c += 64) {
-          const float v0 = (tile[c * pitch + j] - mean) * r * lnw[c] + lnb[c];
-          const float v1 = (tile[(c + 1) * pitch + j] - mean) * r * lnw[c + 1] + lnb[c + 1];
-          *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(v0, v1);
-        }
-      } else {
-        for (int c = lane; c < C; c += 32) o[c] = __float2bfloat16_rn((tile[c * pitch + j] - mean) * r * lnw[c] + lnb[c]);
+    // phase 2a: moments per pixel, nparts threads per pixel, consecutive threads = consecutive pixels (conflict-free
+    // column walks); both moments in one pass, shifted by the pixel's first channel
+    if (part < nparts && pj < npix) {
+      const float piv = tile[pj];
+      float s = 0.f, q = 0.f;
+      for (int c = part; c < C; c += nparts) { const float d = tile[c * pitch + pj] - piv; s += d; q = fmaf(d, d, q); }
+      ps[part * PIX + pj] = s; pq[part * PIX + pj] = q;
+    }
+    __syncthreads();
+    if (tid < npix) {
+      float s = 0.f, q = 0.f;
+      for (int k = 0; k < nparts; ++k) { s += ps[k * PIX + tid]; q += pq[k * PIX + tid]; }
+      const float m = s / C;
+      const float var = fmaxf(q / C - m * m, 0.f);
+      const float mean = tile[tid] + m, r = rsqrtf(var + eps);
+      mean_s[tid] = mean; rstd_s[tid] = r;
+      const size_t pix = (size_t)n * HW + p0 + tid;
+      mu[pix] = mean; rstd[pix] = r;
+    }
+    __syncthreads();
+    // phase 2b: xn rows (NHWC bf16), consecutive threads = consecutive channel pairs of a pixel
+    __nv_bfloat16* orow = xn + ((size_t)n * HW + p0) * C;
+    if ((C & 1) == 0) {
+      const int half = C / 2;
+      for (int idx = tid; idx < npix * half; idx += kThreads) {
+        const int j = idx / half, c = 2 * (idx - j * half);
+        const float mean = mean_s[j], r = rstd_s[j];
+        const float v0 = (tile[c * pitch + j] - mean) * r * lnw_s[c] + lnb_s[c];
+        const float v1 = (tile[(c + 1) * pitch + j] - mean) * r * lnw_s[c + 1] + lnb_s[c + 1];
+        *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * C + c) = __floats2bfloat162_rn(v0, v1);
+      }
+    } else {
+      for (int idx = tid; idx < npix * C; idx += kThreads) {
+        const int j = idx / C, c = idx - j * C;
+        orow[idx] = __float2bfloat16_rn((tile[c * pitch + j] - mean_s[j]) * rstd_s[j] * lnw_s[c] + lnb_s[c]);
       }
     }
   }
@@ -362,8 +389,9 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
   float* rs = mus + PIX;
   float* m1s = rs + PIX;
   float* m2s = m1s + PIX;
-  __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(m2s + PIX);   // [PIX][ge]
-  const uint32_t* gs32 = reinterpret_cast<const uint32_t*>(gs);
+  float* ps1 = m2s + PIX;                      // [kThreads] partial sums of phase 2
+  float* ps2 = ps1 + kThreads;
+  __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(ps2 + kThreads);   // [PIX][ge]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vec_per_row = PIX / VP;
   for (int i = tid; i < 6 * C; i += kThreads) accs[i] = 0.f;
@@ -405,29 +433,27 @@ bn3_sum_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16
       }
     }
     __syncthreads();
-    // phase 2: per pixel m1 = mean_c(g*w), m2 = mean_c(g*w*xhat)
-    for (int j = warp; j < npix; j += kWarps) {
-      const float m = mus[j], r = rs[j];
-      float s1 = 0.f, s2 = 0.f;
-      if ((C & 1) == 0) {
-        for (int cw = lane; cw < C / 2; cw += 32) {
-          const uint32_t raw = gs32[(size_t)j * (ge / 2) + cw];
-          const float2 gx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
-          const int c = 2 * cw;
-          const float xh0 = (tile[c * pitch + j] - m) * r, xh1 = (tile[(c + 1) * pitch + j] - m) * r;
-          const float gg0 = gx.x * lnw_s[c], gg1 = gx.y * lnw_s[c + 1];
-          s1 += gg0 + gg1;
-          s2 = fmaf(gg0, xh0, fmaf(gg1, xh1, s2));
-        }
-      } else {
-        for (int c = lane; c < C; c += 32) {
-          const float gg = bf(gs[(size_t)j * ge + c]) * lnw_s[c];
+    // phase 2: per pixel m1 = mean_c(g*w), m2 = mean_c(g*w*xhat); nparts threads per pixel, consecutive threads =
+    // consecutive pixels (conflict-free walks of the u tile columns and of the odd-pitch gradient rows)
+    {
+      const int nparts = kThreads / PIX;
+      const int pj = tid % PIX, prt = tid / PIX;
+      if (prt < nparts && pj < npix) {
+        const float m = mus[pj], r = rs[pj];
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = prt; c < C; c += nparts) {
+          const float gg = bf(gs[(size_t)pj * ge + c]) * lnw_s[c];
           s1 += gg;
-          s2 = fmaf(gg, (tile[c * pitch + j] - m) * r, s2);
+          s2 = fmaf(gg, (tile[c * pitch + pj] - m) * r, s2);
         }
+        ps1[prt * PIX + pj] = s1; ps2[prt * PIX + pj] = s2;
       }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) { m1s[j] = s1 / C; m2s[j] = s2 / C; }
+      __syncthreads();
+      if (tid < npix) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k < nparts; ++k) { s1 += ps1[k * PIX + tid]; s2 += ps2[k * PIX + tid]; }
+        m1s[tid] = s1 / C; m2s[tid] = s2 / C;
+      }
     }
     __syncthreads();
     // phase 3: du (NCHW bf16) and the six per-channel sums
@@ -595,7 +621,39 @@ __global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, double coun
   }
 }
 
+// out[c] = sum_r part[r][c], rows added in a fixed order (the per-CTA partial rows of the kernels above)
+constexpr int kCsCols = 32, kCsGroups = 16;
+__global__ void __launch_bounds__(kCsCols * kCsGroups)
+colsum_kernel(const float* __restrict__ part, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[kCsGroups][kCsCols + 1];
+  const int tx = threadIdx.x % kCsCols, ty = threadIdx.x / kCsCols;
+  const int c = blockIdx.x * kCsCols + tx;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < cols) {
+    int r = ty;
+    for (; r + kCsGroups < rows; r += 2 * kCsGroups) {
+      a0 += part[(size_t)r * cols + c];
+      a1 += part[(size_t)(r + kCsGroups) * cols + c];
+    }
+    if (r < rows) a0 += part[(size_t)r * cols + c];
+  }
+  red[ty][tx] = a0 + a1;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCsGroups; ++k) t += red[k][tx];
+    out[c] = t;
+  }
+}
+
 // ---- host launchers -------------------------------------------------------------------------
+int colsum(const float* part, int rows, int cols, float* out, cudaStream_t st) {
+  colsum_kernel<<<(cols + kCsCols - 1) / kCsCols, kCsCols * kCsGroups, 0, st>>>(part, rows, cols, out);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
 static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_bytes) {
   Geo g{};
   g.N = N; g.C = C; g.HW = HW;
@@ -667,7 +725,8 @@ int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* 
                    const float* lnw, const float* lnb, float eps, void* xn, float* mu, float* rstd, int N, int C, int HW,
                    cudaStream_t st) {
   size_t smem;
-  Geo g = make_geo(N, C, HW, 0, &smem);
+  Geo g = make_geo(N, C, HW, 2, &smem);              // u tile + lnw + lnb
+  smem += (2 * (size_t)kThreads + 2 * (size_t)g.PIX) * sizeof(float);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
   const int vp = pick_vp(HW, y1, y2, y3, y1);
   const int grid = grid_for(g, smem);
@@ -741,7 +800,7 @@ int residual_bwd(const float* dout, const void* h2, const float* gamma, const fl
 
 static Geo ln_bwd_geo(int N, int C, int HW, size_t* smem) {
   Geo g = make_geo(N, C, HW, 7, smem);              // u tile + accs [6][C] + lnw [C]
-  *smem += 4 * (size_t)g.PIX * sizeof(float) + (size_t)g.PIX * ln_bwd_gpitch(C) * sizeof(__nv_bfloat16);
+  *smem += (4 * (size_t)g.PIX + 2 * (size_t)kThreads) * sizeof(float) + (size_t)g.PIX * ln_bwd_gpitch(C) * sizeof(__nv_bfloat16);
   return g;
 }
 int bn3_sum_ln_bwd_parts(int N, int C, int HW) {

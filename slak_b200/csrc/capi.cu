@@ -36,6 +36,7 @@ int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy
 }
 // block_fused.cu
 namespace blk {
+int colsum(const float* part, int rows, int cols, float* out, cudaStream_t st);
 int bn3_stats_finalize(const float* part, int splits, double* sums_ws, int C, cudaStream_t st);
 int bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
                      float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale, float* shift,
@@ -343,4 +344,10 @@ SLAK_API int slak_layernorm2d_bwd(const void* g, int g_dtype, const void* x, int
   SLAK_REQUIRE(g && x && w && mean && rstd && dx && part && dw && db, SLAK_ERR_BAD_ARG, "null tensor pointer");
   SLAK_REQUIRE(N >= 0 && C > 0 && HW >= 0, SLAK_ERR_BAD_ARG, "bad size N=%d C=%d HW=%d", N, C, HW);
   return layernorm2d_bwd(g, g_dtype, x, x_dtype, w, mean, rstd, dx, part, dw, db, N, C, HW, (cudaStream_t)stream);
+}
+
+// ---- fixed-order column sum of per-CTA partial rows --------------------------------------------
+SLAK_API int slak_colsum_f32(const float* part, int rows, int cols, float* out, void* stream) {
+  SLAK_REQUIRE(part && out && rows > 0 && cols > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::colsum(part, rows, cols, out, (cudaStream_t)stream);
 }
