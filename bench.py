@@ -381,6 +381,13 @@ def run_ours(args):
                 "kernel": "lk3_fwd_tc_kernel<64,16,TMA> (stage-1 fused 51x5 + 5x51 + 5x5 forward, tcgen05)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": prof["count"]}
+        try:    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (not measured live)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "headline_traffic.json")))
+            if B == h["N"]:
+                roof["traffic"] = tr["dram_bytes"]
+                roof["traffic_source"] = f"{tr['source']} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        except Exception:
+            pass
         if prof["count"] > 0 and B == h["N"]:
             us = prof["ms_total"] * 1e3 / prof["count"]
             roof["avg_us"] = us
