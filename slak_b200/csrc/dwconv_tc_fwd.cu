@@ -96,7 +96,7 @@ struct FwdParams {
 // Banded Toeplitz operands of one channel (K-major SWIZZLE_128B): five T1_s tiles at tp, then five [T2_r ; T3_r] tiles.
 template <int T>
 __device__ __forceinline__ void build_toeplitz(uint8_t* tp, const float* w1s, const float* w2s, const float* w3s,
-                                               int KL, int pad, int t0, int nthr) {
+                                               int KL, int pad, int H, int W, int t0, int nthr) {
   using Cfg = FwdCfg<T>;
   constexpr int CH = T / 8;                                  // 16-byte chunks per row that are ever read
   // T1_s[p][h] = w1[h-p+pad][s]
@@ -106,7 +106,7 @@ __device__ __forceinline__ void build_toeplitz(uint8_t* tp, const float* w1s, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int t = (k8 * 8 + j) - p + pad;
-      v[j] = (t >= 0 && t < KL) ? w1s[t * 5 + s] : 0.f;
+      v[j] = (t >= 0 && t < KL && p < H) ? w1s[t * 5 + s] : 0.f;     // output rows beyond the plane stay exactly zero
     }
     *reinterpret_cast<uint4*>(tp + s * (T * 128) + p * 128 + ((k8 ^ (p & 7)) << 4)) =
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -119,13 +119,13 @@ __device__ __forceinline__ void build_toeplitz(uint8_t* tp, const float* w1s, co
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int t = (k8 * 8 + j) - row + pad;
-        v[j] = (t >= 0 && t < KL) ? w2s[r * KL + t] : 0.f;
+        v[j] = (t >= 0 && t < KL && row < W) ? w2s[r * KL + t] : 0.f;   // output columns beyond the plane: zero
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int t = (k8 * 8 + j) - (row - T) + 2;
-        v[j] = (t >= 0 && t < 5) ? w3s[r * 5 + t] : 0.f;
+        v[j] = (t >= 0 && t < 5 && row - T < W) ? w3s[r * 5 + t] : 0.f;
       }
     }
     *reinterpret_cast<uint4*>(tp + Cfg::kToep1 + r * (2 * T * 128) + row * 128 + ((k8 ^ (row & 7)) << 4)) =
@@ -211,7 +211,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     }
     if (tid < 25) w3s[tid] = P.w3[(size_t)c_first * 25 + tid];
     __syncthreads();
-    build_toeplitz<T>(sm + Cfg::kOffToep, w1s, w2s, w3s, KL, pad, tid, kThreads);
+    build_toeplitz<T>(sm + Cfg::kOffToep, w1s, w2s, w3s, KL, pad, H, W, tid, kThreads);
   }
   fence_proxy_async();
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
@@ -448,11 +448,12 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         uint32_t* vb = v + 32;
         auto chunk_nat = [&](int br, int h, const uint32_t* w) {      // columns 32h .. 32h+31 of y2 / y3, row L
           if (want_stats && ok) {
-            float s = 0.f, q = 0.f;
+            // columns >= W of the accumulator are exact zeros (zero Toeplitz rows): no per-element predicate, and
+            // four independent chains instead of one 32-long dependent one
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (32 * h + j < W) { const float f = __uint_as_float(w[j]); s += f; q = fmaf(f, f, q); }
-            st_s[1 + br] += s; st_q[1 + br] += q;
+            for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(w[j]); s[j & 3] += f; q[j & 3] = fmaf(f, f, q[j & 3]); }
+            st_s[1 + br] += (s[0] + s[1]) + (s[2] + s[3]); st_q[1 + br] += (q[0] + q[1]) + (q[2] + q[3]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -463,12 +464,11 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                            pack_bf16(__uint_as_float(w[8 * j + 6]), __uint_as_float(w[8 * j + 7])));
         };
         auto chunk_t = [&](int h, const uint32_t* w) {                // y1^T: column q = row, p = 32h .. 32h+31
-          if (want_stats && n < P.N && row < W) {
-            float s = 0.f, q = 0.f;
+          if (want_stats && n < P.N && row < W) {       // rows p >= H of y1 are exact zeros as well
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int p = 0; p < 32; ++p)
-              if (32 * h + p < H) { const float f = __uint_as_float(w[p]); s += f; q = fmaf(f, f, q); }
-            st_s[0] += s; st_q[0] += q;
+            for (int p = 0; p < 32; ++p) { const float f = __uint_as_float(w[p]); s[p & 3] += f; q[p & 3] = fmaf(f, f, q[p & 3]); }
+            st_s[0] += (s[0] + s[1]) + (s[2] + s[3]); st_q[0] += (q[0] + q[1]) + (q[2] + q[3]);
           }
 #pragma unroll
           for (int p = 0; p < 32; ++p) {
@@ -578,7 +578,7 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
       }
       if (lane < 25) w3s[lane] = P.w3[(size_t)c * 25 + lane];
       __syncwarp();
-      build_toeplitz<T>(tp, w1s, w2s, w3s, KL, pad, lane, 32);
+      build_toeplitz<T>(tp, w1s, w2s, w3s, KL, pad, H, W, lane, 32);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_TP_FULL + set));
