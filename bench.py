@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--width-factor", type=float, default=1.0)
     p.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline step")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--watchdog", type=float, default=1500.0, help="abort the process after this many seconds")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return p.parse_args()
 
@@ -428,6 +429,10 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    # a run that cannot finish (a wedged collective, a dead peer rank) must not hold the GPU box forever
+    _wd = threading.Timer(a.watchdog, lambda: (sys.stderr.write("[bench] watchdog: no result in time, aborting\n"), os._exit(3)))
+    _wd.daemon = True
+    _wd.start()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -86,14 +86,10 @@ def dwconv2d_forward(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     N, C, H, W, kh, kw = _conv_dims(x, w)
     y = torch.empty_like(x)
     lib = _lib.load()
-    timed = False
     with torch.cuda.device(x.device):
         rc = lib.slak_dwconv2d_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, C, H, W, kh, kw,
                                    _lib.dtype_code(x.dtype), _lib.dtype_code(w.dtype),
                                    _lib.current_stream_ptr())
-        if timed:
-            ev[1].record()
-            _prof["events"].append(ev)
     _lib.check(rc, "slak_dwconv2d_fwd")
     _count(1)
     return y

@@ -148,3 +148,21 @@ def test_fused_block_eval_mode_matches_module_path():
         finally:
             slak.FUSED_BLOCK = True
     assert ((y0 - y1).abs().max() / y1.abs().max()).item() < 2e-2
+
+
+def test_colsum_is_fixed_order_column_sum():
+    """slak_colsum_f32 folds per-CTA partial rows: compare with a float64 column sum, twice (bitwise repeatable)."""
+    from slak_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    for rows, cols in [(592, 384), (1, 7), (37, 4608), (888, 12)]:
+        part = torch.randn(rows, cols, device="cuda")
+        outs = []
+        for _ in range(2):
+            out = torch.empty(cols, device="cuda")
+            rc = lib.slak_colsum_f32(part.data_ptr(), rows, cols, out.data_ptr(), _lib.current_stream_ptr())
+            _lib.check(rc, "slak_colsum_f32")
+            outs.append(out.clone())
+        assert torch.equal(outs[0], outs[1])
+        ref = part.double().sum(0)
+        assert torch.allclose(outs[0].double(), ref, rtol=1e-5, atol=1e-4 * rows ** 0.5)
