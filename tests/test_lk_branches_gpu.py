@@ -80,3 +80,41 @@ def test_fused_backward_data_and_filter_match_oracle(case):
     # deterministic (fixed-order reduction)
     dws2 = ops.lk_branches_backward_filter(x.to(DEV), *dyd, KL, 5)
     assert all(torch.equal(a, b) for a, b in zip(dws, dws2))
+
+
+# BatchNorm partial sums gathered in the forward epilogue (slak_block_conv_fwd): [C][6] = (sum, sum of squares) of
+# y1, y2, y3 over (N, H, W), from the fp32 accumulators.  Geometries chosen so that both epilogue groups of a CTA,
+# several CTAs per channel (T = 64) and several channels per CTA (small classes) all contribute.
+STAT_CASES = [(9, 3, 56, 56, 51), (1, 2, 56, 56, 51), (37, 5, 14, 14, 47), (70, 3, 28, 28, 49), (45, 4, 7, 7, 13),
+              (300, 2, 56, 56, 5)]
+
+
+@pytest.mark.parametrize("case", STAT_CASES)
+def test_forward_epilogue_statistics_match_float64_sums(case):
+    from slak_b200 import _lib
+    lib = _lib.load()
+    N, C, H, W, KL = case
+    g = torch.Generator().manual_seed(5 + N + KL)
+    x = torch.randn(N, C, H, W, generator=g).bfloat16().to(DEV)
+    ws = [(torch.randn(C, 1, *k, generator=g) * 0.05).to(DEV) for k in ((KL, 5), (5, KL), (5, 5))]
+    ys = [torch.empty_like(x) for _ in range(3)]
+    sums = torch.empty((C, 6), dtype=torch.float64, device=DEV)
+    need = lib.slak_block_conv_fwd_workspace(N, C, H, W)
+    assert need > 0
+    wsp = torch.empty(need, dtype=torch.uint8, device=DEV)
+    rc = lib.slak_block_conv_fwd(x.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ys[0].data_ptr(),
+                                 ys[1].data_ptr(), ys[2].data_ptr(), sums.data_ptr(), wsp.data_ptr(), wsp.numel(),
+                                 N, C, H, W, KL, _lib.current_stream_ptr())
+    _lib.check(rc, "slak_block_conv_fwd")
+    ref = ops.lk_branches_forward(x, *ws)
+    for i in range(3):
+        assert torch.equal(ys[i], ref[i])                       # same kernel with and without the statistics
+        # oracle for the sums: the fp32 conv of the bf16-rounded operands, accumulated in float64
+        w16 = ws[i].bfloat16().double().cpu()
+        y64 = torch.nn.functional.conv2d(x.double().cpu(), w16, padding=(w16.shape[2] // 2, w16.shape[3] // 2), groups=C)
+        s_ref = y64.sum((0, 2, 3))
+        q_ref = (y64 * y64).sum((0, 2, 3))
+        got = sums.cpu()
+        scale = float(N * H * W) ** 0.5
+        assert torch.allclose(got[:, 2 * i], s_ref, rtol=1e-4, atol=1e-4 * scale), (i, got[:, 2 * i], s_ref)
+        assert torch.allclose(got[:, 2 * i + 1], q_ref, rtol=1e-4, atol=1e-5 * scale)
