@@ -177,6 +177,21 @@ SLAK_API int slak_bn3_finalize_bwd(const float* S, double count, const float* co
 SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef,
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Pointwise MLP of a Block on the tensor cores (models/SLaK.py:157-160, pwconv1 -> GELU -> pwconv2) with the
+ * elementwise passes folded into the GEMM epilogues.  ROUND-2 DRAFT: exported and compiled, not yet validated on
+ * hardware and not used unless SLAK_FUSED_MLP=1 (slak_b200/block.py); the default path keeps cuBLAS.
+ *   fc1_gelu_fwd : h[M,N] = x[M,K] w[N,K]^T + bias (bf16), a = gelu(h)   -- nn.Linear + nn.GELU under autocast
+ *   fc2_dgelu_bwd: dh[M,N] = (g[M,K] wt[N,K]^T) * gelu'(h); colpart[slak_mlp_parts(M,N)][N] fp32 = per-CTA partial
+ *                  column sums of dh (fold with slak_colsum_f32: the bias gradient of pwconv1).  wt = W2^T.
+ * All matrices bf16 row-major, 16-byte aligned; N % 128 == 0, K % 8 == 0, N <= 4096.
+ * ------------------------------------------------------------------------- */
+SLAK_API int slak_mlp_parts(int M, int N);
+SLAK_API int slak_mlp_fc1_gelu_fwd(const void* x, const void* w, const float* bias, void* h, void* a, int M, int N,
+                                   int K, void* stream);
+SLAK_API int slak_mlp_fc2_dgelu_bwd(const void* g, const void* wt, const void* h, void* dh, float* colpart, int M,
+                                    int N, int K, void* stream);
+
 /* out[c] = sum over r of part[r*cols + c], rows added in a fixed order: folds the per-CTA partial rows the
  * *_parts kernels above emit (bias / gamma / LayerNorm-parameter gradients: the column sums the reference gets
  * from autograd's `grad.sum(0)` of nn.Linear / the `gamma * x` broadcast, models/SLaK.py:158-164). */

@@ -52,6 +52,9 @@ SIGNATURES = {
     "slak_bn3_sum_ln_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_vp]),
     "slak_bn3_finalize_bwd": (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "slak_bn3_bwd_apply": (_i, [_vp] * 8 + [_i] * 3 + [_vp]),
+    "slak_mlp_parts": (_i, [_i, _i]),
+    "slak_mlp_fc1_gelu_fwd": (_i, [_vp] * 5 + [_i] * 3 + [_vp]),
+    "slak_mlp_fc2_dgelu_bwd": (_i, [_vp] * 5 + [_i] * 3 + [_vp]),
     "slak_colsum_f32": (_i, [_vp, _i, _i, _vp, _vp]),
     "slak_layernorm2d_fwd": (_i, [_vp, _i, _vp, _vp, ctypes.c_float, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "slak_layernorm2d_bwd_parts": (_i, [_i, _i]),

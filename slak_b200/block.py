@@ -17,6 +17,7 @@ module-by-module path.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -34,6 +35,14 @@ def _ptr3(a, b, c):
 
 def _ck(rc, what):
     _lib.check(rc, what)
+
+
+# round-2 draft of the tcgen05 pointwise MLP (csrc/mlp_tc.cu): opt-in until it has been validated on hardware
+FUSED_MLP = os.environ.get("SLAK_FUSED_MLP", "0") == "1"
+
+
+def _fused_mlp_ok(M, N, K):
+    return N % 128 == 0 and K % 8 == 0 and N <= 4096 and M > 0
 
 
 def _colsum(lib, part2d, st):
@@ -113,8 +122,16 @@ class FusedBlockFunction(torch.autograd.Function):
         # pointwise MLP (cuBLAS): bf16 operands, fp32 accumulate
         W1b, W2b = W1.to(bf16), W2.to(bf16)
         xf = xn.view(N * HW, C)
-        h = torch.addmm(b1.to(bf16), xf, W1b.t())
-        a = F.gelu(h)
+        if FUSED_MLP and _fused_mlp_ok(N * HW, W1b.shape[0], C):
+            # round-2 draft (csrc/mlp_tc.cu): GEMM1 + bias + GELU in one tcgen05 kernel, H and A written once
+            h = torch.empty((N * HW, W1b.shape[0]), dtype=bf16, device=dev)
+            a = torch.empty_like(h)
+            _ck(lib.slak_mlp_fc1_gelu_fwd(_p(xf), _p(W1b), _p(b1.float().contiguous()), _p(h), _p(a), N * HW,
+                                          W1b.shape[0], C, st), "slak_mlp_fc1_gelu_fwd")
+            ops._count(1)
+        else:
+            h = torch.addmm(b1.to(bf16), xf, W1b.t())
+            a = F.gelu(h)
         h2 = torch.addmm(b2.to(bf16), a, W2b.t())
         out = torch.empty_like(x)
         _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), None, N, C, HW, st),
@@ -153,17 +170,28 @@ class FusedBlockFunction(torch.autograd.Function):
         dgamma, db2 = dg2[0], dg2[1]
         # ---- MLP backward (cuBLAS GEMMs + one fused GELU'/bias-gradient pass) -----------------------------
         dW2 = torch.mm(dh2.t(), a).float()
-        da = torch.mm(dh2, W2b)
         K = h.shape[1]
-        parts = lib.slak_gelu_bwd_bias_parts(N * HW, K)
-        hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
-        _ck(lib.slak_gelu_bwd_bias(_p(da), _p(h), _p(da), _p(hp), N * HW, K, st), "slak_gelu_bwd_bias")   # in place
-        dh = da
+        if FUSED_MLP and _fused_mlp_ok(N * HW, K, C):
+            # round-2 draft: dH = (dH2 W2) * gelu'(H) and the bias-gradient partials in the GEMM epilogue
+            parts = lib.slak_mlp_parts(N * HW, K)
+            hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
+            dh = torch.empty_like(h)
+            W2t = W2b.t().contiguous()                 # [4C, C]: K-major B operand
+            _ck(lib.slak_mlp_fc2_dgelu_bwd(_p(dh2), _p(W2t), _p(h), _p(dh), _p(hp), N * HW, K, C, st),
+                "slak_mlp_fc2_dgelu_bwd")
+            ops._count(1)
+        else:
+            da = torch.mm(dh2, W2b)
+            parts = lib.slak_gelu_bwd_bias_parts(N * HW, K)
+            hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
+            _ck(lib.slak_gelu_bwd_bias(_p(da), _p(h), _p(da), _p(hp), N * HW, K, st), "slak_gelu_bwd_bias")   # in place
+            dh = da
+            del da
         db1 = _colsum(lib, hp, st)
         xf = xn.view(N * HW, C)
         dW1 = torch.mm(dh.t(), xf).float()
         dxn = torch.mm(dh, W1b)
-        del dh, da
+        del dh
         # ---- LayerNorm backward + BatchNorm reductions ------------------------------------------------
         parts = lib.slak_bn3_sum_ln_bwd_parts(N, C, HW)
         du = torch.empty_like(xb)

@@ -30,6 +30,10 @@ int lk3_fwd_tc_splits(int N, int C, int H, int W);
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
                const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
                cudaStream_t st);
+int mlp_parts(int M, int N);
+int mlp_fc1_gelu_fwd(const void* x, const void* w, const float* bias, void* h, void* a, int M, int N, int K, cudaStream_t st);
+int mlp_fc2_dgelu_bwd(const void* g, const void* wt, const void* h, void* dh, float* colpart, int M, int N, int K,
+                      cudaStream_t st);
 size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL);
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
@@ -350,4 +354,24 @@ SLAK_API int slak_layernorm2d_bwd(const void* g, int g_dtype, const void* x, int
 SLAK_API int slak_colsum_f32(const float* part, int rows, int cols, float* out, void* stream) {
   SLAK_REQUIRE(part && out && rows > 0 && cols > 0, SLAK_ERR_BAD_ARG, "bad argument");
   return blk::colsum(part, rows, cols, out, (cudaStream_t)stream);
+}
+
+// ---- pointwise MLP GEMMs with fused epilogues (round-2 draft, see csrc/mlp_tc.cu) ------------------
+SLAK_API int slak_mlp_parts(int M, int N) { return tc::mlp_parts(M, N); }
+
+SLAK_API int slak_mlp_fc1_gelu_fwd(const void* x, const void* w, const float* bias, void* h, void* a, int M, int N, int K,
+                                   void* stream) {
+  SLAK_REQUIRE(x && w && bias && h && a, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(bias) |
+                 reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(a)) & 15) == 0, SLAK_ERR_BAD_ARG,
+               "operands must be 16-byte aligned");
+  return tc::mlp_fc1_gelu_fwd(x, w, bias, h, a, M, N, K, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_mlp_fc2_dgelu_bwd(const void* g, const void* wt, const void* h, void* dh, float* colpart, int M, int N,
+                                    int K, void* stream) {
+  SLAK_REQUIRE(g && wt && h && dh && colpart, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(wt) | reinterpret_cast<uintptr_t>(h) |
+                 reinterpret_cast<uintptr_t>(dh)) & 15) == 0, SLAK_ERR_BAD_ARG, "operands must be 16-byte aligned");
+  return tc::mlp_fc2_dgelu_bwd(g, wt, h, dh, colpart, M, N, K, (cudaStream_t)stream);
 }
