@@ -2,8 +2,6 @@
 funcs.py under /root/reference, unmodified) in the authoring container.  The reference cannot
 travel to the GPU box, so the vectors are committed.  Run:  python oracle/gen_golden.py
 """
-import argparse
-import math
 import os
 import sys
 import types

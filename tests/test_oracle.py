@@ -1,7 +1,6 @@
 """The oracle against (a) the reference's own host code (oracle/_ref, built from
 /root/reference), (b) the torch statement the reference's test uses, (c) committed golden
 vectors.  CPU only."""
-import os
 
 import numpy as np
 import pytest

@@ -5,7 +5,6 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch  # noqa: E402
 import bench  # noqa: E402
 
 print("cpu_count", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
