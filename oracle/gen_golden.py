@@ -76,58 +76,82 @@ def gen_model(ref_slak):
     np.savez_compressed(os.path.join(OUT, "ref_slak_narrow.npz"), **out)
 
 
-def gen_masking(ref_slak, ref_sparse):
-    """sparse_core.Masking on CPU: init (uniform / ERK), per-step apply_mask, and three
-    prune-and-grow rounds (magnitude prune, random growth), CPU RNG seeded like main.py:232."""
+# (file tag, init, only_L, prune mode, growth mode); the first four are the SLaK defaults (funcs.py:107-114,170-175)
+MASKING_VARIANTS = [
+    ("uniform_all", "uniform", False, "magnitude", "random"),
+    ("uniform_onlyL", "uniform", True, "magnitude", "random"),
+    ("ERK_all", "ERK", False, "magnitude", "random"),
+    ("ERK_onlyL", "ERK", True, "magnitude", "random"),
+    # the other modes of sparse_core.py:141-261 / funcs.py that slak_b200 mirrors
+    ("snip_all", "snip", False, "magnitude", "random"),
+    ("uniform_all_gradient", "uniform", False, "magnitude", "gradient"),
+    ("uniform_all_momentum", "uniform", False, "magnitude", "momentum"),
+    # prune_mode "SET" cannot be pinned: the reference's magnitude_and_negativity_prune reads a Masking attribute
+    # that does not exist (funcs.py:150 `name2prune_rate`) and raises at the first prune round
+]
+
+
+def gen_masking(ref_slak, ref_sparse, only=None):
+    """sparse_core.Masking on CPU: init (uniform / ERK / snip), per-step apply_mask, and three prune-and-grow
+    rounds per variant, CPU RNG seeded like main.py:232.  `only`: write just the variants whose tag is listed."""
     torch.Tensor.cuda = lambda self, *a, **k: self      # funcs.py:174 calls .cuda() on the CPU draw
-    for init in ("uniform", "ERK"):
-        for only_l in (False, True):
-            torch.manual_seed(0)
-            np.random.seed(0)
-            net = torch.nn.Sequential()
-            net.add_module("stages", torch.nn.Sequential(
-                ref_slak.Block(dim=8, kernel_size=(13, 5), Decom=True, bn=True, layer_scale_init_value=1.0),
-                ref_slak.Block(dim=8, kernel_size=(9, 5), Decom=True, bn=True, layer_scale_init_value=1.0)))
+    for tag, init, only_l, prune_mode, growth_mode in MASKING_VARIANTS:
+        if only is not None and tag not in only:
+            continue
+        torch.manual_seed(0)
+        np.random.seed(0)
+        net = torch.nn.Sequential()
+        net.add_module("stages", torch.nn.Sequential(
+            ref_slak.Block(dim=8, kernel_size=(13, 5), Decom=True, bn=True, layer_scale_init_value=1.0),
+            ref_slak.Block(dim=8, kernel_size=(9, 5), Decom=True, bn=True, layer_scale_init_value=1.0)))
+        for p in net.parameters():
+            if p.dim() > 1:
+                torch.nn.init.normal_(p, std=0.1)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+        args = types.SimpleNamespace(device="cpu", fix=False, update_frequency=2, only_L=only_l,
+                                     sparse_init=init, sparsity=0.4, distributed=False)
+        out = {}
+        loader = None
+        if init == "snip":                               # one batch for SNIP(): per-pixel 8-way classification
+            gl = torch.Generator().manual_seed(7)
+            images = torch.randn(4, 8, 12, 12, generator=gl)
+            labels = torch.randint(0, 8, (4, 12, 12), generator=gl)
+            loader = [(images, labels)]
+            out["snip_images"] = images.numpy().copy()
+            out["snip_labels"] = labels.numpy().copy()
+        T = 12
+        decay = ref_sparse.CosineDecay(0.5, T)
+        mask = ref_sparse.Masking(opt, train_loader=loader, prune_rate_decay=decay, prune_rate=0.5,
+                                  prune_mode=prune_mode, growth_mode=growth_mode, redistribution_mode="none",
+                                  args=args)
+        for n, p in net.named_parameters():
+            out["w_init." + n] = p.detach().numpy().copy()
+        torch.manual_seed(123)                      # the stream Masking.init draws from
+        mask.add_module(net)
+        out["mask_names"] = np.array(sorted(mask.masks.keys()))
+        for n, m in mask.masks.items():
+            out["mask0." + n] = m.numpy().copy()
+        for n, p in net.named_parameters():
+            out["w0." + n] = p.detach().numpy().copy()
+        g = torch.Generator().manual_seed(99)
+        rates = []
+        for step in range(1, 7):
+            # deterministic pseudo-gradients, then the reference's own step()
             for p in net.parameters():
-                if p.dim() > 1:
-                    torch.nn.init.normal_(p, std=0.1)
-            opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
-            args = types.SimpleNamespace(device="cpu", fix=False, update_frequency=2, only_L=only_l,
-                                         sparse_init=init, sparsity=0.4, distributed=False)
-            T = 12
-            decay = ref_sparse.CosineDecay(0.5, T)
-            mask = ref_sparse.Masking(opt, train_loader=None, prune_rate_decay=decay, prune_rate=0.5,
-                                      prune_mode="magnitude", growth_mode="random", redistribution_mode="none",
-                                      args=args)
-            out = {}
-            for n, p in net.named_parameters():
-                out["w_init." + n] = p.detach().numpy().copy()
-            torch.manual_seed(123)                      # the stream Masking.init draws from
-            mask.add_module(net)
-            out["mask_names"] = np.array(sorted(mask.masks.keys()))
+                p.grad = torch.randn(p.shape, generator=g) * 0.05
+            torch.manual_seed(1000 + step)          # stream random_growth draws from
+            mask.step()
+            rates.append(mask.prune_rate)
             for n, m in mask.masks.items():
-                out["mask0." + n] = m.numpy().copy()
+                out[f"mask{step}." + n] = m.numpy().copy()
             for n, p in net.named_parameters():
-                out["w0." + n] = p.detach().numpy().copy()
-            g = torch.Generator().manual_seed(99)
-            rates = []
-            for step in range(1, 7):
-                # deterministic pseudo-gradients, then the reference's own step()
-                for p in net.parameters():
-                    p.grad = torch.randn(p.shape, generator=g) * 0.05
-                torch.manual_seed(1000 + step)          # stream random_growth draws from
-                mask.step()
-                rates.append(mask.prune_rate)
-                for n, m in mask.masks.items():
-                    out[f"mask{step}." + n] = m.numpy().copy()
-                for n, p in net.named_parameters():
-                    out[f"w{step}." + n] = p.detach().numpy().copy()
-                for n, p in net.named_parameters():
-                    st = opt.state[p]
-                    if "momentum_buffer" in st:
-                        out[f"mom{step}." + n] = st["momentum_buffer"].numpy().copy()
-            out["prune_rates"] = np.array(rates)
-            np.savez_compressed(os.path.join(OUT, f"ref_masking_{init}_{'onlyL' if only_l else 'all'}.npz"), **out)
+                out[f"w{step}." + n] = p.detach().numpy().copy()
+            for n, p in net.named_parameters():
+                st = opt.state[p]
+                if "momentum_buffer" in st:
+                    out[f"mom{step}." + n] = st["momentum_buffer"].numpy().copy()
+        out["prune_rates"] = np.array(rates)
+        np.savez_compressed(os.path.join(OUT, f"ref_masking_{tag}.npz"), **out)
 
 
 def gen_conv_grid():
@@ -149,9 +173,12 @@ def gen_conv_grid():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref_slak, ref_sparse, ref_funcs = import_reference()
-    gen_conv_grid()
-    gen_block(ref_slak)
-    gen_model(ref_slak)
-    gen_masking(ref_slak, ref_sparse)
+    if len(sys.argv) > 1 and sys.argv[1] == "masking":      # python oracle/gen_golden.py masking [tag ...]
+        gen_masking(ref_slak, ref_sparse, only=(sys.argv[2:] or None))
+    else:
+        gen_conv_grid()
+        gen_block(ref_slak)
+        gen_model(ref_slak)
+        gen_masking(ref_slak, ref_sparse)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -9,10 +9,13 @@ import torch
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def replay(init, only_l, device):
+def replay(init, only_l, device, prune_mode="magnitude", growth_mode="random"):
     from slak_b200 import slak
     from slak_b200.sparse_core import CosineDecay, Masking
-    z = np.load(os.path.join(GOLD, f"ref_masking_{init}_{'onlyL' if only_l else 'all'}.npz"))
+    tag = f"{init}_{'onlyL' if only_l else 'all'}"
+    if growth_mode != "random":
+        tag += "_" + growth_mode
+    z = np.load(os.path.join(GOLD, f"ref_masking_{tag}.npz"))
     slak.use_sync_bn = False
     net = torch.nn.Sequential()
     net.add_module("stages", torch.nn.Sequential(
@@ -25,10 +28,26 @@ def replay(init, only_l, device):
     opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
     args = types.SimpleNamespace(device=str(device), fix=False, update_frequency=2, only_L=only_l,
                                  sparse_init=init, sparsity=0.4, distributed=False)
-    mask = Masking(opt, train_loader=None, prune_rate_decay=CosineDecay(0.5, 12), prune_rate=0.5,
-                   prune_mode="magnitude", growth_mode="random", redistribution_mode="none", args=args)
+    loader = None
+    if init == "snip":      # the batch SNIP() looked at in the reference run
+        loader = [(torch.from_numpy(z["snip_images"]), torch.from_numpy(z["snip_labels"]))]
+    mask = Masking(opt, train_loader=loader, prune_rate_decay=CosineDecay(0.5, 12), prune_rate=0.5,
+                   prune_mode=prune_mode, growth_mode=growth_mode, redistribution_mode="none", args=args)
     torch.manual_seed(123)
-    mask.add_module(net)
+    if init == "snip" and torch.device(device).type == "cpu":
+        # SNIP() runs one forward/backward of the network.  The product has no CPU depthwise operator (by design), so
+        # on CPU tensors this test lends the model the oracle's conv for that one call; everything Masking itself does
+        # (scores, threshold, layer sparsities, Bernoulli draw) is the code under test
+        from oracle import slak_model as omodel
+        from slak_b200 import ops
+        saved = ops.depthwise_conv2d
+        ops.depthwise_conv2d = omodel.dwconv
+        try:
+            mask.add_module(net)
+        finally:
+            ops.depthwise_conv2d = saved
+    else:
+        mask.add_module(net)
     assert sorted(mask.masks) == sorted(str(s) for s in z["mask_names"])
 
     def check(step):
