@@ -36,8 +36,8 @@ HEADLINE = dict(N=PER_GPU_BATCH, C=96, H=56, W=56, kh=51, kw=5)   # the north-st
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     p.add_argument("--width-factor", type=float, default=1.0)
