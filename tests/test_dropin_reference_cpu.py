@@ -1,0 +1,66 @@
+"""INTEGRATION.md section 1 on the host side: the REFERENCE's own models/SLaK.py and sparse_core.py, imported
+unmodified, pick up slak_b200/dropin/depthwise_conv2d_implicit_gemm.py in place of the CUTLASS extension module.
+Runs only where the reference tree exists (the authoring container); nothing is executed on a GPU."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SLAK_REFERENCE", "/root/reference")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree not present")
+
+SCRIPT = textwrap.dedent("""
+    import sys, types
+    root, ref = sys.argv[1], sys.argv[2]
+    # the drop-in directory in place of the CUTLASS example directory (models/SLaK.py:9-10), then the reference itself
+    sys.path[:0] = [root, root + "/slak_b200/dropin", ref]
+    import importlib, os
+    # oracle/ref_shims also holds a CPU stand-in of the operator module; only its timm package may be visible here
+    shim = types.ModuleType("timm"); shim.__path__ = [root + "/oracle/ref_shims/timm"]
+    sys.modules["timm"] = shim
+    import torch
+    import depthwise_conv2d_implicit_gemm as op
+    assert op.__file__.startswith(root + "/slak_b200/dropin"), op.__file__
+    import models.SLaK as ref_slak
+    assert ref_slak.DepthWiseConv2dImplicitGEMM is op.DepthWiseConv2dImplicitGEMM
+    ref_slak.use_sync_bn = False
+    net = ref_slak.SLaK_tiny(kernel_size=[51, 49, 47, 13, 5], Decom=True, bn=True, width_factor=0.25)
+    from slak_b200.dwconv import DepthWiseConv2dImplicitGEMM
+    convs = [m for m in net.modules() if isinstance(m, DepthWiseConv2dImplicitGEMM)]
+    assert len(convs) == 54 and all(isinstance(m, torch.nn.Conv2d) for m in convs)      # 18 Blocks x 3 branches
+    from slak_b200 import slak
+    slak.use_sync_bn = False
+    ours = slak.SLaK_tiny(kernel_size=[51, 49, 47, 13, 5], Decom=True, bn=True, width_factor=0.25)
+    a, b = net.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    ours.load_state_dict(a)                                 # reference checkpoints load unchanged
+    # the reference's mask engine scans names / shapes of the model built on the drop-in (sparse_core.py:122-130)
+    import sparse_core as ref_sparse
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+    args = types.SimpleNamespace(device="cpu", fix=False, update_frequency=100, only_L=True, sparse_init="uniform",
+                                 sparsity=0.4, distributed=False)
+    mask = ref_sparse.Masking(opt, train_loader=None, prune_rate_decay=ref_sparse.CosineDecay(0.3, 100), prune_rate=0.3,
+                              prune_mode="magnitude", growth_mode="random", redistribution_mode="none", args=args)
+    mask.add_module(net)
+    assert len(mask.masks) == 36 and all("LoRA" in n for n in mask.masks)                # --only-L: the 36 LoRA tensors
+    # without a CUDA device the operator refuses instead of computing on the CPU
+    try:
+        convs[0](torch.zeros(1, convs[0].in_channels, 8, 8))
+    except RuntimeError as e:
+        assert "CUDA" in str(e)
+    else:
+        raise AssertionError("CPU tensor accepted")
+    print("DROPIN_OK")
+""")
+
+
+@pytest.mark.timeout(600)
+def test_reference_model_and_mask_engine_run_on_the_dropin_module():
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, REF], capture_output=True, text=True, timeout=580, cwd=ROOT)
+    assert r.returncode == 0 and "DROPIN_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
