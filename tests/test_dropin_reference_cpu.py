@@ -64,3 +64,40 @@ SCRIPT = textwrap.dedent("""
 def test_reference_model_and_mask_engine_run_on_the_dropin_module():
     r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, REF], capture_output=True, text=True, timeout=580, cwd=ROOT)
     assert r.returncode == 0 and "DROPIN_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+SCRIPT_C = textwrap.dedent("""
+    import sys
+    root, ref = sys.argv[1], sys.argv[2]
+    ext_dir = ref + "/cutlass/examples/19_large_depthwise_conv2d_torch_extension"
+    # only the native module is replaced: a directory holding just our _depthwise_conv2d_implicit_gemm_C stand-in
+    import os, shutil, tempfile
+    tmp = tempfile.mkdtemp()
+    shutil.copy(root + "/slak_b200/dropin/_depthwise_conv2d_implicit_gemm_C.py", tmp)
+    sys.path[:0] = [root, tmp, ext_dir]
+    import torch
+    import depthwise_conv2d_implicit_gemm as ref_op              # the REFERENCE's Python module (autograd + dispatch)
+    assert ref_op.__file__.startswith(ext_dir), ref_op.__file__
+    import _depthwise_conv2d_implicit_gemm_C as native
+    for name in ("forward_fp32", "backward_data_fp32", "backward_filter_fp32",
+                 "forward_fp16", "backward_data_fp16", "backward_filter_fp16"):           # frontend.h:3-10
+        assert callable(getattr(native, name)), name
+    m = ref_op.DepthWiseConv2dImplicitGEMM(8, (13, 5))
+    assert isinstance(m, torch.nn.Conv2d) and tuple(m.weight.shape) == (8, 1, 13, 5)
+    try:
+        m(torch.zeros(1, 8, 16, 16))
+    except RuntimeError as e:
+        assert "CUDA" in str(e)
+    else:
+        raise AssertionError("CPU tensor accepted")
+    print("DROPIN_C_OK")
+""")
+
+
+@pytest.mark.timeout(300)
+def test_reference_python_module_runs_on_the_native_standin():
+    ext = os.path.join(REF, "cutlass", "examples", "19_large_depthwise_conv2d_torch_extension")
+    if not os.path.isdir(ext):
+        pytest.skip("reference extension directory not present")
+    r = subprocess.run([sys.executable, "-c", SCRIPT_C, ROOT, REF], capture_output=True, text=True, timeout=280, cwd=ROOT)
+    assert r.returncode == 0 and "DROPIN_C_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
