@@ -98,8 +98,10 @@ def conv_bn_relu(in_channels, out_channels, kernel_size, stride, padding, groups
 
 def fuse_bn(conv, bn):
     """Fold an eval-mode BN into the conv that feeds it: returns (kernel, bias)."""
-    inv = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-    return conv.weight * inv.reshape(-1, 1, 1, 1), bn.bias - bn.running_mean * inv
+    std = torch.sqrt(bn.running_var + bn.eps)
+    # operation order of models/SLaK.py:56-58, so that merged checkpoints are bit-identical: the bias uses
+    # (mean * gamma) / std, not mean * (gamma / std)
+    return conv.weight * (bn.weight / std).reshape(-1, 1, 1, 1), bn.bias - bn.running_mean * bn.weight / std
 
 
 class ReparamLargeKernelConv(nn.Module):

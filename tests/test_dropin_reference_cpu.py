@@ -101,3 +101,43 @@ def test_reference_python_module_runs_on_the_native_standin():
         pytest.skip("reference extension directory not present")
     r = subprocess.run([sys.executable, "-c", SCRIPT_C, ROOT, REF], capture_output=True, text=True, timeout=280, cwd=ROOT)
     assert r.returncode == 0 and "DROPIN_C_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+SCRIPT_MERGE = textwrap.dedent("""
+    import sys, types
+    root, ref = sys.argv[1], sys.argv[2]
+    sys.path[:0] = [root, root + "/slak_b200/dropin", ref]
+    shim = types.ModuleType("timm"); shim.__path__ = [root + "/oracle/ref_shims/timm"]
+    sys.modules["timm"] = shim
+    import torch
+    import models.SLaK as ref_slak
+    from slak_b200 import slak
+    ref_slak.use_sync_bn = False
+    slak.use_sync_bn = False
+    torch.manual_seed(5)
+    for K, small in ((13, 5), (7, 3), (9, None)):
+        kw = dict(in_channels=6, out_channels=6, kernel_size=K, stride=1, groups=6, small_kernel=small,
+                  small_kernel_merged=False, Decom=False, bn=True)
+        ours = slak.ReparamLargeKernelConv(**kw)
+        for b in ours.branches():                     # non-trivial eval statistics and affine parameters
+            b.bn.running_mean.normal_(); b.bn.running_var.uniform_(0.5, 2.0)
+            b.bn.weight.data.normal_(1, 0.2); b.bn.bias.data.normal_()
+            b.conv.weight.data.normal_(0, 0.1)
+        theirs = ref_slak.ReparamLargeKernelConv(**kw)
+        assert list(theirs.state_dict().keys()) == list(ours.state_dict().keys())
+        theirs.load_state_dict(ours.state_dict())
+        k1, b1 = ours.get_equivalent_kernel_bias()
+        k2, b2 = theirs.get_equivalent_kernel_bias()          # models/SLaK.py:102-109 with fuse_bn :49-58
+        assert torch.equal(k1, k2) and torch.equal(b1, b2), (K, small)
+        ours.merge_kernel(); theirs.merge_kernel()            # models/SLaK.py:111-122
+        assert list(theirs.state_dict().keys()) == list(ours.state_dict().keys()) == ["lkb_reparam.weight", "lkb_reparam.bias"]
+        for k in ours.state_dict():
+            assert torch.equal(ours.state_dict()[k], theirs.state_dict()[k]), (K, small, k)
+    print("MERGE_OK")
+""")
+
+
+@pytest.mark.timeout(300)
+def test_kernel_merge_and_bn_folding_equal_the_reference():
+    r = subprocess.run([sys.executable, "-c", SCRIPT_MERGE, ROOT, REF], capture_output=True, text=True, timeout=280, cwd=ROOT)
+    assert r.returncode == 0 and "MERGE_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
