@@ -231,7 +231,7 @@ def fused_block_supported(block, x) -> bool:
     lk = block.large_kernel
     if not (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous()):
         return False
-    if not (torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16):
+    if not (torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16):
         return False
     if not (getattr(lk, "Decom", False) and hasattr(lk, "small_conv") and hasattr(lk, "LoRA1") and block.gamma is not None):
         return False

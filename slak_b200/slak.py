@@ -202,7 +202,7 @@ class LayerNorm(nn.Module):
             # the stride-2 conv behind a downsampling LayerNorm reads bf16 anyway)
             out_dtype = torch.float32
             if torch.is_autocast_enabled():
-                if self.out_dtype_autocast is not None and torch.get_autocast_gpu_dtype() == self.out_dtype_autocast:
+                if self.out_dtype_autocast is not None and torch.get_autocast_dtype('cuda') == self.out_dtype_autocast:
                     out_dtype = self.out_dtype_autocast
             elif x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16:
                 out_dtype = torch.bfloat16
@@ -244,7 +244,7 @@ class Block(nn.Module):
         if x.is_cuda and torch.is_autocast_enabled():
             # the depthwise branch is autocast-eligible here (the reference pins fp32 inputs to its
             # fp32 kernel, depthwise_conv2d_implicit_gemm.py:16); the residual stream keeps x's dtype
-            x = x.to(torch.get_autocast_gpu_dtype())
+            x = x.to(torch.get_autocast_dtype('cuda'))
         x = self.large_kernel(x)
         x = x.permute(0, 2, 3, 1)
         x = self.norm(x)
