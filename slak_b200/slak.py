@@ -8,8 +8,9 @@ Reference map (models/SLaK.py):
   ReparamLargeKernelConv :60-122                Block :126-166       SLaK :168-235
   LayerNorm :237-261    SLaK_tiny/small/base/large :264-286
 
-Only the Block / large-kernel path is re-implemented natively; stem, downsampling and
-head stay stock PyTorch modules (out of scope).
+The Block / large-kernel path and the channels_first LayerNorm of the stem and downsampling
+layers run on this library's kernels; the strided stem / downsampling convolutions and the head
+stay stock PyTorch modules (out of scope).
 """
 from __future__ import annotations
 
