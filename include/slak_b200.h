@@ -150,7 +150,9 @@ SLAK_API int slak_block_conv_fwd(const void* x, const float* w1, const float* w2
                                  int N, int C, int H, int W, int KL, void* stream);
 /* bnw/bnb/rmean/rvar: HOST arrays of three device pointers (branch K x 5, 5 x K, 5 x 5), each [C];
  * entries of rmean/rvar may be NULL to skip the running-statistics update */
-SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const float* const* bnw,
+/* count_dev (may be NULL): DEVICE pointer to the global element count per channel; when given it overrides `count`
+ * (SyncBN with unequal per-rank batches: the count is all-reduced together with the sums, no host round trip) */
+SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const double* count_dev, const float* const* bnw,
                                    const float* const* bnb, float* const* rmean, float* const* rvar, float eps,
                                    float momentum, int C, float* scale, float* shift, float* mean, float* istd,
                                    void* stream);
@@ -172,7 +174,10 @@ SLAK_API int slak_bn3_sum_ln_bwd_parts(int N, int C, int HW);
 SLAK_API int slak_bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3,
                                  const float* scale, const float* shift, const float* lnw, const float* mu,
                                  const float* rstd, void* du, float* part, int N, int C, int HW, void* stream);
-SLAK_API int slak_bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean,
+/* S = GLOBAL sums (dy coefficients); S_local (NULL = S) = this rank's sums, from which dbnw/dbnb are taken: like
+ * torch's SyncBatchNorm the parameter gradients are per-rank and the data-parallel wrapper averages them */
+SLAK_API int slak_bn3_finalize_bwd(const float* S, const float* S_local, double count, const double* count_dev,
+                                   const float* const* bnw, const float* mean,
                                    const float* istd, int C, float* coef, float* dbnw, float* dbnb, void* stream);
 SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef,
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);

@@ -40,7 +40,7 @@ SIGNATURES = {
     "slak_lk_branches_bwd_filter": (_i, [_vp] * 7 + [_i] * 7 + [_vp, _sz, _vp]),
     "slak_block_conv_fwd_workspace": (_sz, [_i] * 4),
     "slak_block_conv_fwd": (_i, [_vp] * 9 + [_sz] + [_i] * 5 + [_vp]),
-    "slak_bn3_finalize_fwd": (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
+    "slak_bn3_finalize_fwd": (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
     "slak_bn3_eval_affine": (_i, [_vp] * 4 + [ctypes.c_float, _i, _vp, _vp, _vp]),
     "slak_bn3_sum_ln_fwd": (_i, [_vp] * 7 + [ctypes.c_float] + [_vp] * 3 + [_i] * 3 + [_vp]),
     "slak_block_residual_fwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
@@ -50,7 +50,7 @@ SIGNATURES = {
     "slak_gelu_bwd_bias": (_i, [_vp] * 4 + [_i64, _i, _vp]),
     "slak_bn3_sum_ln_bwd_parts": (_i, [_i] * 3),
     "slak_bn3_sum_ln_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_vp]),
-    "slak_bn3_finalize_bwd": (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "slak_bn3_finalize_bwd": (_i, [_vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "slak_bn3_bwd_apply": (_i, [_vp] * 8 + [_i] * 3 + [_vp]),
     "slak_mlp_parts": (_i, [_i, _i]),
     "slak_mlp_fc1_gelu_fwd": (_i, [_vp] * 5 + [_i] * 3 + [_vp]),

@@ -54,16 +54,22 @@ def _colsum(lib, part2d, st):
     return out
 
 
-def _dist_world():
+def _dist_world(group=None):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
-        return dist, dist.get_world_size()
+        return dist, dist.get_world_size(group)
     return None, 1
 
 
 class FusedBlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, w2, w3, bw1, bw2, bw3, bb1, bb2, bb3, lnw, lnb, W1, b1, W2, b2, gamma, dp, cfg):
+        with torch.cuda.device(x.device):
+            return FusedBlockFunction._forward(ctx, x, w1, w2, w3, bw1, bw2, bw3, bb1, bb2, bb3, lnw, lnb, W1, b1, W2, b2,
+                                               gamma, dp, cfg)
+
+    @staticmethod
+    def _forward(ctx, x, w1, w2, w3, bw1, bw2, bw3, bb1, bb2, bb3, lnw, lnb, W1, b1, W2, b2, gamma, dp, cfg):
         lib = _lib.load()
         st = _lib.current_stream_ptr()
         N, C, H, W = x.shape
@@ -78,7 +84,9 @@ class FusedBlockFunction(torch.autograd.Function):
         training = cfg["training"]
         sync = cfg["sync_bn"]
         if training:
-            sums = torch.empty((C, 6), dtype=torch.float64, device=dev)
+            # [C][6] sums, then one extra slot: this rank's element count per channel (SyncBN all-reduces both)
+            sums_buf = torch.empty((C * 6 + 1,), dtype=torch.float64, device=dev)
+            sums = sums_buf[:C * 6]
             need = lib.slak_block_conv_fwd_workspace(N, C, H, W)
             ws = ops._workspace(need, dev)
             timed = ops._profiled(N, C, H, W, KL, 5, bf16)
@@ -91,14 +99,18 @@ class FusedBlockFunction(torch.autograd.Function):
                 ev[1].record()
                 ops._prof["events"].append(ev)
             count = float(N * HW)
-            dist, world = _dist_world() if sync else (None, 1)
+            count_dev = None
+            dist, world = _dist_world(cfg["process_group"]) if sync else (None, 1)
             if world > 1:                     # SyncBatchNorm: statistics over the global batch
-                dist.all_reduce(sums)
-                count *= world
+                # the true per-rank counts are summed with the statistics (ranks may hold different batch sizes,
+                # torch/nn/modules/_functions.py:33-60) and stay on the device: no host round trip, graph-capturable
+                sums_buf[C * 6:].fill_(count)
+                dist.all_reduce(sums_buf, group=cfg["process_group"])
+                count_dev = sums_buf[C * 6:]
             mean = torch.empty((3, C), dtype=torch.float32, device=dev)
             istd = torch.empty((3, C), dtype=torch.float32, device=dev)
             rm, rv = cfg["running_mean"], cfg["running_var"]
-            _ck(lib.slak_bn3_finalize_fwd(_p(sums), count, _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3), _ptr3(*rm),
+            _ck(lib.slak_bn3_finalize_fwd(_p(sums), count, _p(count_dev), _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3), _ptr3(*rm),
                                           _ptr3(*rv), cfg["bn_eps"], cfg["bn_momentum"], C, _p(scale), _p(shift),
                                           _p(mean), _p(istd), st), "slak_bn3_finalize_fwd")
             for nbt in cfg["num_batches_tracked"]:
@@ -113,6 +125,7 @@ class FusedBlockFunction(torch.autograd.Function):
                                          cfg["bn_eps"], C, _p(scale), _p(shift), st), "slak_bn3_eval_affine")
             mean = istd = None
             count = float(N * HW)
+            count_dev = None
             ops._count(1)
         xn = torch.empty((N, H, W, C), dtype=bf16, device=dev)
         mu = torch.empty((N * HW,), dtype=torch.float32, device=dev)
@@ -139,6 +152,7 @@ class FusedBlockFunction(torch.autograd.Function):
         ops._count(2)
         ctx.cfg = cfg
         ctx.count = count
+        ctx.count_dev = count_dev
         ctx.dims = (N, C, H, W, KL)
         ctx.save_for_backward(xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd,
                               xn, h, a, h2, W1b, W2b, gamma, dp)
@@ -146,6 +160,11 @@ class FusedBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        with torch.cuda.device(dout.device):
+            return FusedBlockFunction._backward(ctx, dout)
+
+    @staticmethod
+    def _backward(ctx, dout):
         (xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd, xn, h, a, h2, W1b, W2b,
          gamma, dp) = ctx.saved_tensors
         cfg = ctx.cfg
@@ -201,14 +220,19 @@ class FusedBlockFunction(torch.autograd.Function):
         red = _colsum(lib, part.view(parts, 6 * C), st).view(6, C)
         dlnw, dlnb = red[0], red[1]
         S = red[2:6].contiguous()
+        S_local = None
         if cfg["sync_bn"]:
-            dist, world = _dist_world()
+            dist, world = _dist_world(cfg["process_group"])
             if world > 1:
-                dist.all_reduce(S)
+                # dy needs the GLOBAL sums; the BN weight / bias gradients are taken from this rank's own sums, as
+                # torch's SyncBatchNorm does (its all-reduce comes after grad_weight / grad_bias), so that the
+                # data-parallel gradient average gives global_sum / world and not the global sum itself
+                S_local = S.clone()
+                dist.all_reduce(S, group=cfg["process_group"])
         coef = torch.empty((9, C), dtype=torch.float32, device=dev)
         dbnw = torch.empty((3, C), dtype=torch.float32, device=dev)
         dbnb = torch.empty((3, C), dtype=torch.float32, device=dev)
-        _ck(lib.slak_bn3_finalize_bwd(_p(S), ctx.count, _ptr3(bw1, bw2, bw3), _p(mean), _p(istd), C, _p(coef),
+        _ck(lib.slak_bn3_finalize_bwd(_p(S), _p(S_local), ctx.count, _p(ctx.count_dev), _ptr3(bw1, bw2, bw3), _p(mean), _p(istd), C, _p(coef),
                                       _p(dbnw), _p(dbnb), st), "slak_bn3_finalize_bwd")
         dy1, dy2, dy3 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
         _ck(lib.slak_bn3_bwd_apply(_p(du), _p(y1), _p(y2), _p(y3), _p(coef), _p(dy1), _p(dy2), _p(dy3), N, C, HW, st),
@@ -242,7 +266,17 @@ def fused_block_supported(block, x) -> bool:
     N, C, H, W = x.shape
     if C > 1024 or block.norm.data_format != "channels_last":
         return False
-    if not all(bn.affine and bn.weight.dtype == torch.float32 for bn in (lk.LoRA1.bn, lk.LoRA2.bn, lk.small_conv.bn)):
+    bns = (lk.LoRA1.bn, lk.LoRA2.bn, lk.small_conv.bn)
+    if not all(bn.affine and bn.weight.dtype == torch.float32 for bn in bns):
+        return False
+    # the fused node implements exactly one BatchNorm configuration for the three branches; anything a user may have
+    # changed on an individual BN (frozen bn.eval() inside a training Block, cumulative averaging with momentum=None,
+    # mixed eps/momentum, SyncBatchNorm on some branches only) goes through the module-by-module path
+    if not all(bn.training == block.training and bn.momentum is not None for bn in bns):
+        return False
+    if len({(float(bn.eps), float(bn.momentum), bool(bn.track_running_stats), type(bn)) for bn in bns}) != 1:
+        return False
+    if isinstance(bns[0], torch.nn.SyncBatchNorm) and len({id(bn.process_group) for bn in bns}) != 1:
         return False
     return ops.lk_branches_uses_tc(_Shape(N, C, H, W), lk.kernel_size, 5)
 
@@ -262,8 +296,8 @@ def fused_block_forward(block, x):
     track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)
     training = block.training or not track
     cfg = {
-        "training": training, "sync_bn": sync,
-        "bn_eps": float(bns[0].eps), "bn_momentum": float(bns[0].momentum if bns[0].momentum is not None else 0.1),
+        "training": training, "sync_bn": sync, "process_group": getattr(bns[0], "process_group", None) if sync else None,
+        "bn_eps": float(bns[0].eps), "bn_momentum": float(bns[0].momentum),
         "ln_eps": float(block.norm.eps),
         "running_mean": tuple(bn.running_mean if (track and block.training) or not training else None for bn in bns),
         "running_var": tuple(bn.running_var if (track and block.training) or not training else None for bn in bns),

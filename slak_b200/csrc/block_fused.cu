@@ -561,11 +561,13 @@ __global__ void bn3_reduce_partials_kernel(const float* __restrict__ part, int s
 // out: scale[3][C], shift[C], mean[3][C], istd[3][C]
 struct P3 { const float* p[3]; };
 struct M3 { float* p[3]; };
-__global__ void bn3_finalize_fwd_kernel(const double* __restrict__ sums, double count, P3 bnw, P3 bnb, M3 rmean, M3 rvar,
+__global__ void bn3_finalize_fwd_kernel(const double* __restrict__ sums, double count, const double* __restrict__ count_dev,
+                                        P3 bnw, P3 bnb, M3 rmean, M3 rvar,
                                         float eps, float momentum, int C, float* __restrict__ scale,
                                         float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ istd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (count_dev) count = *count_dev;            // SyncBN: the all-reduced number of elements per channel
   float sh = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -601,12 +603,18 @@ __global__ void bn3_eval_affine_kernel(P3 bnw, P3 bnb, P3 rmean, P3 rvar, float 
   shift[c] = sh;
 }
 // S: [4][C] = sum du, sum du*y_i (global) ; out coef [9][C], dbnw[3][C], dbnb[3][C]
-__global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, double count, P3 bnw,
+// S_local (may be NULL = S): this rank's own sums.  The parameter gradients come from them, as torch's SyncBatchNorm
+// takes grad_weight / grad_bias before its all-reduce (torch/nn/modules/_functions.py:140-160) and leaves their
+// averaging to the data-parallel wrapper; the dy coefficients need the global sums.
+__global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, const float* __restrict__ S_local, double count,
+                                        const double* __restrict__ count_dev, P3 bnw,
                                         const float* __restrict__ mean, const float* __restrict__ istd, int C,
                                         float* __restrict__ coef, float* __restrict__ dbnw, float* __restrict__ dbnb) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double S0 = S[c];
+  if (count_dev) count = *count_dev;
+  if (!S_local) S_local = S;
+  const double S0 = S[c], L0 = S_local[c];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double m = mean[i * C + c], is = istd[i * C + c], w = bnw.p[i][c];
@@ -616,8 +624,8 @@ __global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, double coun
     coef[i * C + c] = (float)a;
     coef[(3 + i) * C + c] = (float)(-a * is * D / count);
     coef[(6 + i) * C + c] = (float)(-a * S0 / count + a * is * m * D / count);
-    dbnw[i * C + c] = (float)D;
-    dbnb[i * C + c] = (float)S0;
+    dbnw[i * C + c] = (float)(is * ((double)S_local[(i + 1) * C + c] - m * L0));
+    dbnb[i * C + c] = (float)L0;
   }
 }
 
@@ -697,12 +705,12 @@ int bn3_stats_finalize(const float* part, int splits, double* sums_ws, int C, cu
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
-int bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
-                     float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale, float* shift,
-                     float* mean, float* istd, cudaStream_t st) {
+int bn3_finalize_fwd(const double* sums, double count, const double* count_dev, const float* const* bnw,
+                     const float* const* bnb, float* const* rmean, float* const* rvar, float eps, float momentum, int C,
+                     float* scale, float* shift, float* mean, float* istd, cudaStream_t st) {
   P3 w{{bnw[0], bnw[1], bnw[2]}}, b{{bnb[0], bnb[1], bnb[2]}};
   M3 rm{{rmean[0], rmean[1], rmean[2]}}, rv{{rvar[0], rvar[1], rvar[2]}};
-  bn3_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, count, w, b, rm, rv, eps, momentum, C, scale, shift, mean, istd);
+  bn3_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, count, count_dev, w, b, rm, rv, eps, momentum, C, scale, shift, mean, istd);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
@@ -713,10 +721,10 @@ int bn3_eval_affine(const float* const* bnw, const float* const* bnb, const floa
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
-int bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean, const float* istd, int C,
-                     float* coef, float* dbnw, float* dbnb, cudaStream_t st) {
+int bn3_finalize_bwd(const float* S, const float* S_local, double count, const double* count_dev, const float* const* bnw,
+                     const float* mean, const float* istd, int C, float* coef, float* dbnw, float* dbnb, cudaStream_t st) {
   P3 w{{bnw[0], bnw[1], bnw[2]}};
-  bn3_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(S, count, w, mean, istd, C, coef, dbnw, dbnb);
+  bn3_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(S, S_local, count, count_dev, w, mean, istd, C, coef, dbnw, dbnb);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }

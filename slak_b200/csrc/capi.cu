@@ -42,12 +42,12 @@ int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy
 namespace blk {
 int colsum(const float* part, int rows, int cols, float* out, cudaStream_t st);
 int bn3_stats_finalize(const float* part, int splits, double* sums_ws, int C, cudaStream_t st);
-int bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
+int bn3_finalize_fwd(const double* sums, double count, const double* count_dev, const float* const* bnw, const float* const* bnb,
                      float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale, float* shift,
                      float* mean, float* istd, cudaStream_t st);
 int bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean, const float* const* rvar,
                     float eps, int C, float* scale, float* shift, cudaStream_t st);
-int bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean, const float* istd, int C,
+int bn3_finalize_bwd(const float* S, const float* S_local, double count, const double* count_dev, const float* const* bnw, const float* mean, const float* istd, int C,
                      float* coef, float* dbnw, float* dbnb, cudaStream_t st);
 int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, const float* shift,
                    const float* lnw, const float* lnb, float eps, void* xn, float* mu, float* rstd, int N, int C, int HW,
@@ -241,12 +241,12 @@ SLAK_API int slak_block_conv_fwd(const void* x, const float* w1, const float* w2
   return blk::bn3_stats_finalize((const float*)workspace, tc::lk3_fwd_tc_splits(N, C, H, W), sums, C, st);
 }
 
-SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const float* const* bnw, const float* const* bnb,
+SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const double* count_dev, const float* const* bnw, const float* const* bnb,
                                    float* const* rmean, float* const* rvar, float eps, float momentum, int C,
                                    float* scale, float* shift, float* mean, float* istd, void* stream) {
-  SLAK_REQUIRE(sums && bnw && bnb && rmean && rvar && scale && shift && mean && istd && C > 0 && count > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  SLAK_REQUIRE(sums && bnw && bnb && rmean && rvar && scale && shift && mean && istd && C > 0 && (count > 0 || count_dev), SLAK_ERR_BAD_ARG, "bad argument");
   for (int i = 0; i < 3; ++i) SLAK_REQUIRE(bnw[i] && bnb[i], SLAK_ERR_BAD_ARG, "null BN parameter");
-  return blk::bn3_finalize_fwd(sums, count, bnw, bnb, rmean, rvar, eps, momentum, C, scale, shift, mean, istd, (cudaStream_t)stream);
+  return blk::bn3_finalize_fwd(sums, count, count_dev, bnw, bnb, rmean, rvar, eps, momentum, C, scale, shift, mean, istd, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean,
@@ -295,10 +295,10 @@ SLAK_API int slak_bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2
   return blk::bn3_sum_ln_bwd(dxn, y1, y2, y3, scale, shift, lnw, mu, rstd, du, part, N, C, HW, (cudaStream_t)stream);
 }
 
-SLAK_API int slak_bn3_finalize_bwd(const float* S, double count, const float* const* bnw, const float* mean, const float* istd,
+SLAK_API int slak_bn3_finalize_bwd(const float* S, const float* S_local, double count, const double* count_dev, const float* const* bnw, const float* mean, const float* istd,
                                    int C, float* coef, float* dbnw, float* dbnb, void* stream) {
-  SLAK_REQUIRE(S && bnw && bnw[0] && bnw[1] && bnw[2] && mean && istd && coef && dbnw && dbnb && C > 0 && count > 0, SLAK_ERR_BAD_ARG, "bad argument");
-  return blk::bn3_finalize_bwd(S, count, bnw, mean, istd, C, coef, dbnw, dbnb, (cudaStream_t)stream);
+  SLAK_REQUIRE(S && bnw && bnw[0] && bnw[1] && bnw[2] && mean && istd && coef && dbnw && dbnb && C > 0 && (count > 0 || count_dev), SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::bn3_finalize_bwd(S, S_local, count, count_dev, bnw, mean, istd, C, coef, dbnw, dbnb, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3, const float* coef,

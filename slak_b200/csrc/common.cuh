@@ -9,6 +9,13 @@
 
 namespace slak {
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 // ---- thread-local error message ------------------------------------------------
 void set_error(const char* fmt, ...);
 
@@ -22,14 +29,15 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
-// raise a kernel's dynamic shared-memory limit once per call site (not on every launch: the attribute
-// call must not happen while a CUDA graph is being captured more often than needed)
+// raise a kernel's dynamic shared-memory limit once per call site AND DEVICE (cudaFuncSetAttribute is per device;
+// not on every launch: the attribute call must not happen while a CUDA graph is being captured more often than needed)
 #define SLAK_SET_MAX_SMEM(kern, bytes)                                                             \
   do {                                                                                             \
-    static int _slak_cur_smem = 0;                                                                 \
-    if ((int)(bytes) > _slak_cur_smem) {                                                           \
+    static int _slak_cur_smem[slak::kMaxDevices] = {0};                                            \
+    const int _slak_dev = slak::current_device();                                                  \
+    if ((int)(bytes) > _slak_cur_smem[_slak_dev]) {                                                \
       SLAK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
-      _slak_cur_smem = (int)(bytes);                                                               \
+      _slak_cur_smem[_slak_dev] = (int)(bytes);                                                    \
     }                                                                                              \
   } while (0)
 
@@ -58,13 +66,12 @@ template <typename T> __device__ __forceinline__ float round_to(float v) { retur
 static inline int dtype_size(int dtype) { return dtype == SLAK_F32 ? 4 : 2; }
 
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 }  // namespace slak
