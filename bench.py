@@ -25,12 +25,26 @@ if ROOT not in sys.path:
 import torch
 import torch.nn.functional as F
 
-KERNEL_SIZE = [51, 49, 47, 13, 5]
-DEPTHS = [3, 3, 9, 3]
-PER_GPU_BATCH = 128
-IMG = 224
 NUM_CLASSES = 1000
-HEADLINE = dict(N=PER_GPU_BATCH, C=96, H=56, W=56, kh=51, kw=5)   # the north-star kernel
+# one metric string for BOTH arms (the driver refuses to form a ratio otherwise); `dtype` says what each arm computes in
+METRIC = "SLaK-T 51x51 224x224 bf16 training images/sec"
+# SURVEY.md section 8(d) "Config 1..5" (= BASELINE.json configs[0..4]); config 1 is the CPU plumbing case (tests/)
+CONFIGS = {
+    2: dict(model="SLaK_tiny", depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], kernel_size=[51, 49, 47, 13, 5], img=224,
+            batch=128, update_freq=1, sparse=False, metric=METRIC,
+            what="SLaK-T 51x51 224x224 bf16 fwd+bwd+AdamW, batch 128/GPU (BASELINE.json configs[1])"),
+    3: dict(model="SLaK_tiny", depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], kernel_size=[51, 49, 47, 13, 5], img=224,
+            batch=128, update_freq=4, sparse=False, metric="SLaK-T 51x51 224x224 bf16 DDP training images/sec (global batch 4096 at 8 GPUs)",
+            what="SLaK-T 51x51 224x224 bf16 data-parallel training, 128/GPU x update_freq 4 (README.md:103-115; global "
+                 "batch 4096 on 8 GPUs), one gradient all-reduce per optimizer step (BASELINE.json configs[2])"),
+    4: dict(model="SLaK_base", depths=[3, 3, 27, 3], dims=[128, 256, 512, 1024], kernel_size=[51, 49, 47, 13, 5], img=384,
+            batch=32, update_freq=1, sparse=False, metric="SLaK-B 51x51 384x384 bf16 training images/sec",
+            what="SLaK-B 51x51 384x384 bf16 fwd+bwd+AdamW, batch 32/GPU (README.md:131; BASELINE.json configs[3])"),
+    5: dict(model="SLaK_tiny", depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], kernel_size=[61, 59, 57, 13, 5], img=224,
+            batch=128, update_freq=1, sparse=True, metric="SLaK-T 61x61 224x224 bf16 sparse (prune-grow every 100 steps) training images/sec",
+            what="SLaK-T 61x61 224x224 bf16, sparse_core.Masking(sparsity 0.4, snip init, magnitude prune, random growth, "
+                 "prune_rate 0.3, update_frequency 100): mask.step() on the timed path (engine.py:79-88; BASELINE.json configs[4])"),
+}
 
 
 def parse():
@@ -39,13 +53,19 @@ def parse():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    p.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="SURVEY.md section 8(d) config number")
+    p.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     p.add_argument("--width-factor", type=float, default=1.0)
-    p.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline step")
+    p.add_argument("--cpu-batch", type=int, default=0, help="images per CPU-arm step (0 = sized so the run takes ~2 min)")
+    p.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUTLASS ext (oracle/_ref/ext) on the GPU")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--watchdog", type=float, default=1500.0, help="abort the process after this many seconds")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    return p.parse_args()
+    a = p.parse_args()
+    a.cfg = CONFIGS[a.config]
+    if a.batch is None:
+        a.batch = a.cfg["batch"]
+    return a
 
 
 # ---------------------------------------------------------------------------------------
@@ -120,8 +140,14 @@ def host_cores():
     return max(1, min(n, 64))
 
 
-def cpu_training_step_factory(width_factor, batch):
-    """Returns (step_fn, cores): one fwd+bwd+AdamW step of SLaK-T on the host cores through the
+def build_model(cfg, width_factor, drop_path_rate):
+    from slak_b200 import slak
+    return getattr(slak, cfg["model"])(kernel_size=cfg["kernel_size"], Decom=True, bn=True, drop_path_rate=drop_path_rate,
+                                       width_factor=width_factor, num_classes=NUM_CLASSES)
+
+
+def cpu_training_step_factory(cfg, width_factor, batch):
+    """Returns (step_fn, cores): one fwd+bwd+AdamW step of the config's model on the host cores through the
     oracle's functional restatement of models/SLaK.py (F.conv2d depthwise, train-mode BN)."""
     from oracle import slak_model as omodel
     from slak_b200 import slak
@@ -129,8 +155,7 @@ def cpu_training_step_factory(width_factor, batch):
     torch.set_num_threads(cores)     # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     torch.manual_seed(0)
     slak.use_sync_bn = False
-    net = slak.SLaK_tiny(kernel_size=KERNEL_SIZE, Decom=True, bn=True, drop_path_rate=0.0,
-                         width_factor=width_factor, num_classes=NUM_CLASSES)
+    net = build_model(cfg, width_factor, 0.0)
     sd = {}
     leaves = []
     for k, v in net.state_dict().items():
@@ -140,11 +165,11 @@ def cpu_training_step_factory(width_factor, batch):
             leaves.append(t)
         sd[k] = t
     opt = torch.optim.AdamW(leaves, lr=1e-3, weight_decay=0.05)
-    x = torch.randn(batch, 3, IMG, IMG)
+    x = torch.randn(batch, 3, cfg["img"], cfg["img"])
     y = torch.randint(0, NUM_CLASSES, (batch,))
 
     def step():
-        out = omodel.forward(x, sd, DEPTHS, training=True)
+        out = omodel.forward(x, sd, cfg["depths"], training=True)
         loss = F.cross_entropy(out, y)
         loss.backward()
         opt.step()
@@ -154,8 +179,19 @@ def cpu_training_step_factory(width_factor, batch):
     return step, cores
 
 
-def time_cpu(width_factor, batch, steps, warmup):
-    step, cores = cpu_training_step_factory(width_factor, batch)
+def cpu_sample_batch(cfg, width_factor, total_steps, budget_s=110.0):
+    """Images per CPU step such that `total_steps` steps take about `budget_s`: one probe step at batch 4 gives the
+    host's images/s (the CPU arm is a BOUNDED SAMPLE of the workload, the per-step batch is reported)."""
+    step, _ = cpu_training_step_factory(cfg, width_factor, 4)
+    step()
+    t0 = time.perf_counter()
+    step()
+    ips = 4.0 / (time.perf_counter() - t0)
+    return max(2, min(32, int(budget_s * ips / max(total_steps, 1))))
+
+
+def time_cpu(cfg, width_factor, batch, steps, warmup):
+    step, cores = cpu_training_step_factory(cfg, width_factor, batch)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -166,18 +202,24 @@ def time_cpu(width_factor, batch, steps, warmup):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (nn.Conv2d semantics) on the box's host cores, through the
+    oracle's restatement of models/SLaK.py (the reference's Python files cannot travel to the GPU box; the restatement
+    is pinned by goldens generated from them, oracle/gen_golden.py).  Same metric / config / steps / warmup as the
+    CUDA arm; every step is a bounded sample (a smaller batch) of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
-    warmup = max(1, min(args.warmup, 1))
-    ips, cores, sps = time_cpu(args.width_factor, args.cpu_batch, steps, warmup)
-    sample = f"{steps} steps x {args.cpu_batch} images of the same SLaK-T 224^2 fwd+bwd+AdamW step, fp32, {cores} threads"
+    cfg = args.cfg
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    batch = args.cpu_batch or cpu_sample_batch(cfg, args.width_factor, steps + warmup)
+    ips, cores, sps = time_cpu(cfg, args.width_factor, batch, steps, warmup)
+    sample = (f"{steps} timed + {warmup} warm-up steps x {batch} images (not {args.batch}: bounded sample) of the same "
+              f"{cfg['model']} {cfg['img']}^2 fwd+bwd+AdamW step through oracle/slak_model.py (F.conv2d depthwise), fp32, {cores} threads")
     line = {
-        "impl": "reference", "metric": "SLaK-T 51x51 224x224 training images/sec", "value": ips, "unit": "images/s",
+        "impl": "reference", "metric": cfg["metric"], "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": dict(workload_config(args, args.gpus), cpu_images_per_step=batch),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -186,20 +228,82 @@ def run_reference(args):
 
 
 def workload_config(args, n):
+    cfg = args.cfg
     return {
-        "workload": f"SLaK-T kernel_size={KERNEL_SIZE} Decom=True bn=True width_factor={args.width_factor} "
-                    f"224x224, fwd+bwd+AdamW, batch {args.batch}/GPU (BASELINE.json configs[1])",
-        "global_batch": args.batch * n, "per_gpu_batch": args.batch, "parallelism": f"dp{n}",
+        "workload": f"config {args.config}: {cfg['what']}; {cfg['model']} kernel_size={cfg['kernel_size']} Decom=True bn=True "
+                    f"width_factor={args.width_factor}",
+        "global_batch": args.batch * n * cfg["update_freq"], "per_gpu_batch": args.batch, "update_freq": cfg["update_freq"],
+        "parallelism": f"dp{n}",
         "autocast": "bf16 (fp32 master weights, fp32 residual stream as in the reference's AMP flow)",
         "l2": "no explicit flush: one step streams >10 GB of activations, far above the 126 MB L2",
     }
 
 
 # ---------------------------------------------------------------------------------------
+# per-kernel roofline table from the CUDA events the fused Block records around its kernel groups
+# ---------------------------------------------------------------------------------------
+def roofline_table(tagged, peak_gbs, peak_tflops, replays):
+    """tagged: [(tag, key, ev0, ev1)] recorded once per launch inside the step (graph: external events, re-read after
+    each replay).  Returns one row per (kernel group, geometry) with the average duration, the ALGORITHMIC bytes or
+    flops of the group and the fraction of the measured peak."""
+    groups = {}
+    for tag, key, e0, e1 in tagged:
+        groups.setdefault((tag, key), []).append((e0, e1))
+    rows = []
+    for (tag, key), evs in groups.items():
+        us = sum(a.elapsed_time(b) for a, b in evs) * 1e3 / len(evs)
+        row = {"kernel": tag, "launches_per_step": len(evs), "avg_us": round(us, 2)}
+        if tag.startswith("dw_"):
+            N, C, H, W, KL = key
+            e = N * C * H * W
+            taps = C * (2 * KL * 5 + 25) * 4
+            if tag == "dw_fwd":        # x read once, y1..y3 written once (bf16) + taps
+                b, what = 4 * e * 2 + taps, "lk3_fwd_tc_kernel (+ statistics fold): 4 tensor passes bf16"
+            elif tag == "dw_dgrad":    # dy1..dy3 bf16 in, shortcut gradient fp32 in, dx fp32 out
+                b, what = e * (3 * 2 + 4 + 4) + taps, "lk_dgrad_tc_kernel x2: 3 bf16 reads + fp32 addend read + fp32 write"
+            else:                      # x, dy1..dy3 bf16 in, dw out
+                b, what = 4 * e * 2 + taps, "lk3_wgrad_tc_kernel (+ reduce): 4 tensor passes bf16"
+            row.update(geometry=f"N{N} C{C} {H}x{W} K{KL}", bound="hbm", algorithmic_bytes=b,
+                       achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
+                       what=what)
+        else:                          # pointwise MLP groups: tensor pipe
+            M, Cc = key
+            fl = {"mlp_fwd": 2, "mlp_bwd": 4}[tag] * 2 * M * Cc * 4 * Cc
+            row.update(geometry=f"M{M} C{Cc} 4C{4 * Cc}", bound="tensor", algorithmic_flops=fl,
+                       achieved=round(fl / (us * 1e-6) / 1e12, 1), unit="TFLOP/s",
+                       frac=round(fl / (us * 1e-6) / 1e12 / peak_tflops, 4),
+                       what="pwconv1+GELU+pwconv2 forward (2 GEMMs)" if tag == "mlp_fwd" else "their backward (4 GEMMs)")
+        rows.append(row)
+    rows.sort(key=lambda r: (r["kernel"], r["geometry"]))
+    return rows
+
+
+def ref_ext_leg(args):
+    """North-star comparison target: the reference's own CUTLASS example-19 operator built for sm_100a
+    (oracle/build_ref_ext.py -> oracle/_ref/ext) under stock PyTorch, timed on this GPU in a subprocess (its wrappers
+    call exit() on any CUDA error).  Returns the dict tools/ref_ext_bench.py prints, or a reason string."""
+    import subprocess
+    so = os.path.join(ROOT, "oracle", "_ref", "ext", "_depthwise_conv2d_implicit_gemm_C.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/ext not built (python oracle/build_ref_ext.py)"}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_ext_bench.py"), "--model-only",
+                            "--config", str(args.config), "--batch", str(args.batch), "--steps", "3"],
+                           capture_output=True, text=True, timeout=420)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": f"rc {r.returncode}: {(r.stderr or r.stdout)[-300:]}"}
+    except Exception as ex:       # noqa: BLE001
+        return {"unavailable": f"{type(ex).__name__}: {ex}"}
+
+
+# ---------------------------------------------------------------------------------------
 # this repo's CUDA path
 # ---------------------------------------------------------------------------------------
 def run_ours(args):
-    from slak_b200 import _lib, ops, slak
+    from slak_b200 import _lib, ddp, ops, slak
+    cfg = args.cfg
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -219,44 +323,57 @@ def run_ours(args):
 
     torch.manual_seed(0 + rank)    # main.py:232 seeds seed + rank
     slak.use_sync_bn = world > 1
-    net = slak.SLaK_tiny(kernel_size=KERNEL_SIZE, Decom=True, bn=True, drop_path_rate=0.1,
-                         width_factor=args.width_factor, num_classes=NUM_CLASSES).to(dev)
+    net = build_model(cfg, args.width_factor, 0.1).to(dev)
     net.train()
     params = [p for p in net.parameters()]
-    if world > 1:                      # identical initial weights on every rank (what DDP's constructor does)
-        for p in params:
-            dist.broadcast(p.data, src=0)
-        for b_ in net.buffers():
-            dist.broadcast(b_, src=0)
+    UF = cfg["update_freq"]
+    # data parallelism = gradient all-reduce only (main.py:374-376): flat gradient buffer, buckets all-reduced on a side
+    # stream as backward produces them (slak_b200/ddp.py); identical initial weights by broadcast
+    dp = ddp.GradientAllReducer(net, bucket_mb=25.0) if world > 1 else None
     opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
 
     B = args.batch
-    x_host = torch.randn(B, 3, IMG, IMG).pin_memory()
-    y_host = torch.randint(0, NUM_CLASSES, (B,)).pin_memory()
+    IMG = cfg["img"]
+    x_host = torch.randn(UF * B, 3, IMG, IMG).pin_memory()
+    y_host = torch.randint(0, NUM_CLASSES, (UF * B,)).pin_memory()
     x_dev = x_host.to(dev)             # static input buffers (also the CUDA-graph inputs)
     y_dev = y_host.to(dev)
 
-    def allreduce_grads():
-        """Data parallelism = gradient all-reduce only (main.py:374-376 wraps DDP for the same effect): one NCCL
-        all-reduce over NVLink of the flattened fp32 gradients, averaged."""
-        grads = [p.grad for p in params if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat)
-        flat.div_(world)
-        for g_, f_ in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g_.copy_(f_)
+    mask = None
+    if cfg["sparse"]:
+        import types
+        from slak_b200.sparse_core import CosineDecay, Masking
+        margs = types.SimpleNamespace(device=str(dev), fix=False, update_frequency=100, only_L=False, sparse_init="snip",
+                                      sparsity=0.4, distributed=world > 1)
+        nb = min(B, 32)
+        loader = [(x_host[:nb], y_host[:nb])]      # SNIP takes one batch (sparse_core.py:11-47)
+        torch.manual_seed(0)                       # same CPU RNG stream on every rank; rank 0's masks win anyway
+        mask = Masking(opt, train_loader=loader, prune_rate_decay=CosineDecay(0.3, 100000), prune_rate=0.3,
+                       prune_mode="magnitude", growth_mode="random", redistribution_mode="none", args=margs)
+        margs.distributed = False                  # SNIP's `sampler.set_epoch` is for a real DistributedSampler
+        mask.add_module(net)
+        margs.distributed = world > 1
 
     def step_eager():
-        # optimizer.zero_grad() as in engine.py:74-86 (set_to_none is the torch default): backward then writes fresh gradients instead of
-        # accumulating into zeroed ones; under graph capture they live in the graph's private pool
-        opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = net(x_dev)
-            loss = F.cross_entropy(out.float(), y_dev)
-        loss.backward()
-        if world > 1:
-            allreduce_grads()
+        # optimizer.zero_grad() as in engine.py:74-86: under graph capture the gradients live in the graph's private pool
+        if dp is None:
+            opt.zero_grad(set_to_none=True)
+        else:
+            dp.zero_grad()
+        for k in range(UF):                              # engine.py:52-80: loss /= update_freq, backward every micro-step
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(x_dev[k * B:(k + 1) * B])
+                loss = F.cross_entropy(out.float(), y_dev[k * B:(k + 1) * B])
+                if UF > 1:
+                    loss = loss / UF
+            if dp is not None:
+                dp.arm(last_micro_step=(k == UF - 1))
+            loss.backward()
+        if dp is not None:
+            dp.finish()
         opt.step()
+        if mask is not None:
+            mask.apply_mask()                            # Masking.step() = optimizer.step(); apply_mask(); advance()
         return loss
 
     def barrier():
@@ -274,20 +391,21 @@ def run_ours(args):
     barrier()
 
     graph, static_loss, graph_note = None, None, "eager (no CUDA graph)"
-    prof_events = []
+    tagged = []
     use_graph = not args.no_graph
+    launches_per_step = None
     if use_graph:
         try:
-            ops.profile_reset(dict(HEADLINE, external_events=True))
+            ops.profile_reset(dict(all=True, external_events=True))
             l_before = ops.launch_count()
             graph = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread's event queries must not invalidate this thread's capture
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = step_eager()
-            prof_events = list(ops._prof["events"])
+            tagged = list(ops._prof["tagged"])
             launches_per_step = ops.launch_count() - l_before
             ops.profile_reset(None)
-            graph_note = "whole step (fwd+bwd+grad all-reduce+AdamW) captured in one CUDA graph and replayed"
+            graph_note = "whole step (fwd+bwd+bucketed grad all-reduce+AdamW) captured in one CUDA graph and replayed"
         except Exception as ex:      # capture not possible on this software stack: fall back to eager launches
             graph, static_loss = None, None
             ops.profile_reset(None)
@@ -304,8 +422,12 @@ def run_ours(args):
     def run_step():
         if graph is not None:
             graph.replay()
-            return static_loss
-        return step_eager()
+            out = static_loss
+        else:
+            out = step_eager()
+        if mask is not None:
+            mask.advance()           # prune-rate schedule; every 100 steps: prune + grow (eager launches, CPU RNG)
+        return out
 
     for _ in range(3):
         run_step()
@@ -313,7 +435,7 @@ def run_ours(args):
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------
     if graph is None:
-        ops.profile_reset(HEADLINE)
+        ops.profile_reset(dict(all=True))
     sampler = ClockSampler(local_rank)
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -326,25 +448,39 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    peak_tf = peaks.get("bf16_tflops_sustained", 1450.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained)" if "hbm_gbs" in peaks else \
+        "fallback 6650 GB/s, 1450 TFLOP/s (B200_PROFILING.md)"
     if graph is None:
         launches = ops.launch_count() - launches0
-        prof = ops.profile_collect()
+        torch.cuda.synchronize()
+        table = roofline_table(ops._prof["tagged"], peak, peak_tf, args.steps)
         ops.profile_reset(None)
-        prof_how = "CUDA events around each launch of the kernel inside the timed region (eager launches)"
+        prof_how = "CUDA events around each kernel group inside the timed region (eager launches)"
     else:
-        launches = launches_per_step * args.steps      # kernels of this repo inside each replayed step graph
-        # the events sit inside the captured graph: read them after the last timed replay and after a few more
-        tot, cnt = 0.0, 0
+        launches = launches_per_step * args.steps + (ops.launch_count() - launches0)
+        # the events sit inside the captured graph: read them after the last timed replay and after 3 further replays
+        acc = []
         for rep in range(4):
             if rep:
-                run_step()
-                torch.cuda.synchronize()
-            for a_, b_ in prof_events:
-                tot += a_.elapsed_time(b_)
-                cnt += 1
-        prof = {"count": cnt, "ms_total": tot}
-        prof_how = ("CUDA events (external) recorded around the kernel INSIDE the captured step graph; read after the "
-                    "last timed replay and 3 further replays")
+                graph.replay()
+            torch.cuda.synchronize()
+            acc.append(roofline_table(tagged, peak, peak_tf, 1))
+        table = acc[0]
+        for r_i, row in enumerate(table):
+            us = sum(a[r_i]["avg_us"] for a in acc) / len(acc)
+            scale = row["avg_us"] / us if us > 0 else 1.0
+            row["avg_us"] = round(us, 2)
+            row["achieved"] = round(row["achieved"] * scale, 1)
+            row["frac"] = round(row["frac"] * scale, 4)
+        prof_how = ("CUDA events (external) recorded around each kernel group INSIDE the captured step graph; read after "
+                    "the last timed replay and 3 further replays")
 
     # ---- timed region 2: end to end through the public API with host buffers --------------
     barrier()
@@ -363,42 +499,34 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    total_images = B * world * args.steps
+    total_images = UF * B * world * args.steps
     value = total_images / (ms / 1e3)
     e2e = total_images / (ms_e2e / 1e3)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        h = HEADLINE
-        # fused three-branch forward: x read once, y1/y2/y3 written once (bf16) + the fp32 taps
-        alg_bytes = 4 * h["N"] * h["C"] * h["H"] * h["W"] * 2 + h["C"] * (2 * h["kh"] * h["kw"] + 25) * 4
+        step_ms = ms / args.steps
+        for row in table:
+            row["share_of_step"] = round(row["avg_us"] * 1e-3 * row["launches_per_step"] / step_ms, 4)
+        head = next((r for r in table if r["kernel"] == "dw_fwd" and " 56x56 " in r["geometry"] + " "), None) or \
+            next((r for r in table if r["kernel"] == "dw_fwd"), None)
         roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "kernel": "lk3_fwd_tc_kernel<64,16,TMA> (stage-1 fused 51x5 + 5x51 + 5x5 forward, tcgen05)",
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": prof["count"]}
+                "kernel": "lk3_fwd_tc_kernel (stage-1 fused K x 5 + 5 x K + 5 x 5 depthwise forward, tcgen05) + its "
+                          "statistics fold, the dominant-shape depthwise kernel of the step",
+                "peak_source": peak_src, "timing": prof_how}
+        if head is not None:
+            roof.update(achieved=head["achieved"], frac=head["frac"], avg_us=head["avg_us"], geometry=head["geometry"],
+                        algorithmic_bytes_per_launch=head["algorithmic_bytes"], launches_timed=head["launches_per_step"],
+                        share_of_step=head["share_of_step"])
         try:    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (not measured live)
             tr = json.load(open(os.path.join(ROOT, "profiles", "headline_traffic.json")))
-            if B == h["N"]:
+            if args.config == 2 and B == 128:
                 roof["traffic"] = tr["dram_bytes"]
                 roof["traffic_source"] = f"{tr['source']} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
         except Exception:
             pass
-        if prof["count"] > 0 and B == h["N"]:
-            us = prof["ms_total"] * 1e3 / prof["count"]
-            roof["avg_us"] = us
-            roof["achieved"] = alg_bytes / (us * 1e-6) / 1e9
-            roof["frac"] = roof["achieved"] / peak
-            roof["share_of_step"] = (us * 1e-3 * 3) / (ms / args.steps)     # 3 stage-1 Blocks per step
-            roof["timing"] = prof_how
         line = {
-            "metric": "SLaK-T 51x51 224x224 bf16 training images/sec", "value": value, "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "metric": cfg["metric"], "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), launch=graph_note),
             "clocks": clocks,
@@ -406,13 +534,26 @@ def run_ours(args):
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": roof,
+            "roofline_all": table,
         }
+        if mask is not None:
+            line["config"]["masking"] = {"steps": mask.steps, "prune_grow_events_total": mask.steps // 100,
+                                         "masked_tensors": len(mask.masks)}
         if world == 1 and not args.no_cpu_baseline:
-            ips, cores, _ = time_cpu(args.width_factor, args.cpu_batch, 3, 1)
+            cb = args.cpu_batch or cpu_sample_batch(cfg, args.width_factor, 4, budget_s=20.0)
+            ips, cores, _ = time_cpu(cfg, args.width_factor, cb, 3, 1)
             line["cpu_baseline"] = {
                 "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                "sample": f"3 steps x {args.cpu_batch} images of the same SLaK-T 224^2 fwd+bwd+AdamW step through "
+                "sample": f"3 steps x {cb} images of the same {cfg['model']} {IMG}^2 fwd+bwd+AdamW step through "
                           f"oracle/slak_model.py (F.conv2d depthwise, fp32), {cores} threads"}
+    if world == 1 and rank == 0 and not args.no_ref_ext:
+        # free this process's GPU memory first: the reference model needs most of the card at batch 128
+        del graph, static_loss
+        opt = net = x_dev = y_dev = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        line["reference_cutlass_ext"] = ref_ext_leg(args)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         # tear down without ncclCommDestroy: with the step graph (which holds the captured all-reduces) alive the
@@ -420,8 +561,6 @@ def run_ours(args):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        if graph is not None:
-            graph.reset()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

@@ -89,15 +89,9 @@ class FusedBlockFunction(torch.autograd.Function):
             sums = sums_buf[:C * 6]
             need = lib.slak_block_conv_fwd_workspace(N, C, H, W)
             ws = ops._workspace(need, dev)
-            timed = ops._profiled(N, C, H, W, KL, 5, bf16)
-            if timed:
-                ev = (ops._new_event(), ops._new_event())
-                ev[0].record()
-            _ck(lib.slak_block_conv_fwd(_p(xb), _p(w1), _p(w2), _p(w3), _p(y1), _p(y2), _p(y3), _p(sums), _p(ws),
-                                        ws.numel(), N, C, H, W, KL, st), "slak_block_conv_fwd")
-            if timed:
-                ev[1].record()
-                ops._prof["events"].append(ev)
+            with ops.timed("dw_fwd", (N, C, H, W, KL)):
+                _ck(lib.slak_block_conv_fwd(_p(xb), _p(w1), _p(w2), _p(w3), _p(y1), _p(y2), _p(y3), _p(sums), _p(ws),
+                                            ws.numel(), N, C, H, W, KL, st), "slak_block_conv_fwd")
             count = float(N * HW)
             count_dev = None
             dist, world = _dist_world(cfg["process_group"]) if sync else (None, 1)
@@ -242,10 +236,12 @@ class FusedBlockFunction(torch.autograd.Function):
         # ---- depthwise branches: fused tensor-core dgrad / wgrad ------------------------------------------
         dx = torch.empty_like(dout)               # shortcut + branch gradient, fp32, written by the dgrad epilogue
         tmp = torch.empty_like(dy3)
-        _ck(lib.slak_lk_branches_bwd_data_f32(_p(dy1), _p(dy2), _p(dy3), _p(w1), _p(w2), _p(w3), _p(dout), _p(dx),
-                                              _p(tmp), N, C, H, W, KL, 5, st), "slak_lk_branches_bwd_data_f32")
+        with ops.timed("dw_dgrad", (N, C, H, W, KL)):
+            _ck(lib.slak_lk_branches_bwd_data_f32(_p(dy1), _p(dy2), _p(dy3), _p(w1), _p(w2), _p(w3), _p(dout), _p(dx),
+                                                  _p(tmp), N, C, H, W, KL, 5, st), "slak_lk_branches_bwd_data_f32")
         ops._count(2)
-        dw1, dw2, dw3 = ops.lk_branches_backward_filter(xb, dy1, dy2, dy3, KL, 5)
+        with ops.timed("dw_wgrad", (N, C, H, W, KL)):
+            dw1, dw2, dw3 = ops.lk_branches_backward_filter(xb, dy1, dy2, dy3, KL, 5)
         return (dx, dw1, dw2, dw3, dbnw[0], dbnw[1], dbnw[2], dbnb[0], dbnb[1], dbnb[2], dlnw, dlnb,
                 dW1, db1, dW2, db2, dgamma, None, None)
 

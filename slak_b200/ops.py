@@ -31,7 +31,7 @@ _ws_cache: dict = {}
 
 # ---- instrumentation used by bench.py (launch accounting + CUDA-event timing of one kernel) ----
 _launches = 0
-_prof = {"match": None, "events": []}
+_prof = {"match": None, "events": [], "tagged": []}
 
 
 def launch_count() -> int:
@@ -45,9 +45,37 @@ def _count(n: int) -> None:
 
 
 def profile_reset(match) -> None:
-    """match = dict(N,C,H,W,kh,kw) of the forward launches to bracket with CUDA events, or None."""
+    """match = dict(N,C,H,W,kh,kw) of the forward launches to bracket with CUDA events, or None.
+    match["all"] = True additionally brackets every depthwise / pointwise-MLP kernel group of the fused Block
+    (see `timed`), collected in _prof["tagged"] as (tag, key, start_event, end_event)."""
     _prof["match"] = match
     _prof["events"] = []
+    _prof["tagged"] = []
+
+
+class timed:
+    """`with ops.timed("dw_fwd", (N, C, H, W, KL)):` -- CUDA events around a kernel group when bench.py asked for the
+    per-kernel roofline table (profile_reset({"all": True, ...})); free otherwise.  The events may sit inside a
+    CUDA-graph capture (external events)."""
+
+    __slots__ = ("tag", "key", "ev")
+
+    def __init__(self, tag, key):
+        self.tag, self.key, self.ev = tag, key, None
+
+    def __enter__(self):
+        m = _prof["match"]
+        if m is not None and m.get("all"):
+            self.ev = _new_event()
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            e1 = _new_event()
+            e1.record()
+            _prof["tagged"].append((self.tag, self.key, self.ev, e1))
+        return False
 
 
 def _new_event():
@@ -65,7 +93,7 @@ def profile_collect():
 
 def _profiled(N, C, H, W, kh, kw, dtype):
     m = _prof["match"]
-    return (m is not None and dtype == torch.bfloat16 and
+    return (m is not None and "N" in m and dtype == torch.bfloat16 and
             (N, C, H, W, kh, kw) == (m["N"], m["C"], m["H"], m["W"], m["kh"], m["kw"]))
 
 

@@ -211,6 +211,12 @@ class Masking(object):
     def step(self):
         self.optimizer.step()
         self.apply_mask()
+        self.advance()
+
+    def advance(self):
+        """The host part of step() (sparse_core.py:303-313) after optimizer.step() and apply_mask(): prune-rate
+        schedule, step counter, prune-and-grow every `update_frequency` steps.  Split out so that a caller who replays
+        `optimizer.step(); apply_mask()` inside a CUDA graph can run the schedule around the replays."""
         self.prune_rate_decay.step()
         self.prune_rate = self.prune_rate_decay.get_dr(self.prune_rate)
         self.steps += 1

@@ -37,6 +37,23 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the driver forms the ours/reference ratio only when both arms print the SAME metric string, and checks steps/warmup
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["metric"] == bench.METRIC == bench.CONFIGS[2]["metric"]
+    assert d["steps"] == 1 and d["warmup"] == 1                      # honoured, not silently capped
+    assert d["config"]["cpu_images_per_step"] == 1 and "1 images" in d["cpu_baseline"]["sample"]
+
+
+def test_every_config_names_the_baseline_entry_and_shares_metric_between_arms():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert sorted(bench.CONFIGS) == [2, 3, 4, 5]
+    for k, c in bench.CONFIGS.items():
+        assert f"configs[{k - 1}]" in c["what"] and c["metric"].endswith("images/sec") or "images/sec" in c["metric"]
+    assert bench.CONFIGS[5]["kernel_size"][0] == 61 and bench.CONFIGS[5]["sparse"]
+    assert bench.CONFIGS[4]["img"] == 384 and bench.CONFIGS[4]["batch"] == 32
+    assert bench.CONFIGS[3]["update_freq"] == 4
 
 
 def test_reference_arm_other_ranks_do_nothing():

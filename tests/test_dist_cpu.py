@@ -47,14 +47,24 @@ def _worker(rank, world, port, q):
             mask.step()                               # includes prune-and-grow every 2 steps, rank-dependent RNG
         sig1 = torch.cat([m.flatten() for m in mask.masks.values()]).clone()
         w = torch.cat([p.detach().flatten() for p in net.parameters()])
-        # flattened gradient all-reduce (bench.py:allreduce_grads)
-        grads = [torch.full((3, 2), float(rank + 1)), torch.full((5,), 10.0 * (rank + 1))]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat)
-        flat.div_(world)
-        for g_, f_ in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g_.copy_(f_)
-        q.put((rank, sig0.numpy(), sig1.numpy(), w.numpy(), [g_.numpy() for g_ in grads]))
+        # bucketed gradient all-reduce of the package (slak_b200/ddp.py; main.py:374-376 semantics): rank-dependent
+        # data, two micro-steps of accumulation, tiny buckets so that several are reduced during backward
+        from slak_b200.ddp import GradientAllReducer
+        torch.manual_seed(300 + rank)
+        mlp = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        dp = GradientAllReducer(mlp, bucket_mb=1e-4)           # broadcasts rank 0's weights
+        wts = torch.cat([p.detach().flatten() for p in mlp.parameters()]).clone()
+        assert len(dp.buckets) >= 2
+        xs = [torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * rank + k)) for k in range(2)]
+        dp.zero_grad()
+        for k in range(2):
+            dp.arm(last_micro_step=(k == 1))
+            (mlp(xs[k]).pow(2).sum() / 2).backward()
+        dp.finish()
+        assert dp.reduced_buckets == len(dp.buckets)
+        assert all(p.grad.data_ptr() >= dp.flat.data_ptr() for p in mlp.parameters())     # still views of the flat buffer
+        grads = [p.grad.detach().clone() for p in mlp.parameters()]
+        q.put((rank, sig0.numpy(), sig1.numpy(), w.numpy(), [g_.numpy() for g_ in grads], wts.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -72,8 +82,20 @@ def test_masks_follow_rank0_and_grads_average_under_gloo():
         p.join(30)
         assert p.exitcode == 0
     import numpy as np
-    (_, a0, a1, wa, ga), (_, b0, b1, wb, gb) = out
+    (_, a0, a1, wa, ga, pa), (_, b0, b1, wb, gb, pb) = out
     assert np.array_equal(a0, b0) and np.array_equal(a1, b1)  # rank 1 holds rank 0's masks after init and after prune/grow
     assert 0 < a1.sum() < a1.size
     assert np.array_equal(wa, wb)                             # hence identical masked weights
-    assert np.allclose(ga[0], 1.5) and np.allclose(gb[1], 15.0)
+    assert np.array_equal(pa, pb)                             # GradientAllReducer broadcast rank 0's weights
+    # every rank ends with the same (averaged) gradients, equal to the single-process mean over both ranks' data
+    for x, y in zip(ga, gb):
+        assert np.array_equal(x, y)
+    torch.manual_seed(300)
+    mlp = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    tot = 0.0
+    for r in range(2):
+        for k in range(2):
+            tot = tot + mlp(torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * r + k))).pow(2).sum() / 2
+    (tot / 2).backward()
+    for g_, p_ in zip(ga, mlp.parameters()):
+        assert np.allclose(g_, p_.grad.numpy(), rtol=1e-5, atol=1e-6)
