@@ -394,16 +394,22 @@ def run_ours(args):
     tagged = []
     use_graph = not args.no_graph
     launches_per_step = None
+    prof_graph = None
     if use_graph:
         try:
-            ops.profile_reset(dict(all=True, external_events=True))
             l_before = ops.launch_count()
             graph = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread's event queries must not invalidate this thread's capture
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = step_eager()
-            tagged = list(ops._prof["tagged"])
             launches_per_step = ops.launch_count() - l_before
+            # the same step once more WITH CUDA events around every kernel group: replayed only outside the timed
+            # regions, for the per-kernel roofline table (the ~100 event nodes cost ~0.5 ms per replay)
+            ops.profile_reset(dict(all=True, external_events=True))
+            prof_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(prof_graph, capture_error_mode="thread_local"):
+                step_eager()
+            tagged = list(ops._prof["tagged"])
             ops.profile_reset(None)
             graph_note = "whole step (fwd+bwd+bucketed grad all-reduce+AdamW) captured in one CUDA graph and replayed"
         except Exception as ex:      # capture not possible on this software stack: fall back to eager launches
@@ -434,8 +440,6 @@ def run_ours(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------
-    if graph is None:
-        ops.profile_reset(dict(all=True))
     sampler = ClockSampler(local_rank)
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -459,19 +463,22 @@ def run_ours(args):
         "fallback 6650 GB/s, 1450 TFLOP/s (B200_PROFILING.md)"
     if graph is None:
         launches = ops.launch_count() - launches0
+        ops.profile_reset(dict(all=True))
+        for _ in range(2):
+            step_eager()
         torch.cuda.synchronize()
-        table = roofline_table(ops._prof["tagged"], peak, peak_tf, args.steps)
+        table = roofline_table(ops._prof["tagged"], peak, peak_tf, 2)
         ops.profile_reset(None)
-        prof_how = "CUDA events around each kernel group inside the timed region (eager launches)"
+        prof_how = "CUDA events around each kernel group in 2 eager steps right after the timed region"
     else:
         launches = launches_per_step * args.steps + (ops.launch_count() - launches0)
         # the events sit inside the captured graph: read them after the last timed replay and after 3 further replays
         acc = []
-        for rep in range(4):
-            if rep:
-                graph.replay()
+        for rep in range(5):
+            prof_graph.replay()
             torch.cuda.synchronize()
-            acc.append(roofline_table(tagged, peak, peak_tf, 1))
+            if rep:                               # the first replay warms the caches of the instrumented graph
+                acc.append(roofline_table(tagged, peak, peak_tf, 1))
         table = acc[0]
         for r_i, row in enumerate(table):
             us = sum(a[r_i]["avg_us"] for a in acc) / len(acc)
@@ -479,8 +486,8 @@ def run_ours(args):
             row["avg_us"] = round(us, 2)
             row["achieved"] = round(row["achieved"] * scale, 1)
             row["frac"] = round(row["frac"] * scale, 4)
-        prof_how = ("CUDA events (external) recorded around each kernel group INSIDE the captured step graph; read after "
-                    "the last timed replay and 3 further replays")
+        prof_how = ("CUDA events (external) recorded around each kernel group INSIDE a second capture of the same step "
+                    "graph, replayed 4 times right after the timed region (the timed graph carries no events)")
 
     # ---- timed region 2: end to end through the public API with host buffers --------------
     barrier()
@@ -548,7 +555,7 @@ def run_ours(args):
                           f"oracle/slak_model.py (F.conv2d depthwise, fp32), {cores} threads"}
     if world == 1 and rank == 0 and not args.no_ref_ext:
         # free this process's GPU memory first: the reference model needs most of the card at batch 128
-        del graph, static_loss
+        del graph, static_loss, prof_graph
         opt = net = x_dev = y_dev = None
         torch.cuda.synchronize()
         torch.cuda.empty_cache()

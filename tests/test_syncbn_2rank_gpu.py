@@ -66,6 +66,19 @@ def _run(blk, x, cot, fused):
     return y.detach().float().cpu(), xi.grad.float().cpu(), grads, bufs
 
 
+def _np(res):
+    """numpy copies for the multiprocessing queue (torch tensors would travel as file descriptors that die with the
+    worker process)."""
+    y, dx, g, b = res
+    return y.numpy(), dx.numpy(), {k: v.numpy() for k, v in g.items()}, {k: v.numpy() for k, v in b.items()}
+
+
+def _pt(res):
+    y, dx, g, b = res
+    t = torch.from_numpy
+    return t(y), t(dx), {k: t(v) for k, v in g.items()}, {k: t(v) for k, v in b.items()}
+
+
 def _worker(rank, world, port, split, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -79,7 +92,7 @@ def _worker(rank, world, port, split, q):
         res = {}
         for fused in (True, False):
             blk = _make_block(sync=True)
-            res[fused] = _run(blk, xs, cs, fused)
+            res[fused] = _np(_run(blk, xs, cs, fused))
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -104,7 +117,7 @@ def test_fused_block_syncbn_two_ranks_equals_full_batch(split):
         assert p.exitcode == 0
     rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
     for fused in (True, False):
-        (y0, dx0, g0, b0), (y1, dx1, g1, b1) = got[0][fused], got[1][fused]
+        (y0, dx0, g0, b0), (y1, dx1, g1, b1) = _pt(got[0][fused]), _pt(got[1][fused])
         tag = "fused" if fused else "module-by-module (torch.nn.SyncBatchNorm)"
         tol = 2e-2 if fused else 5e-2        # the module path rounds y_i and the BN outputs to bf16 separately
         assert rel(torch.cat([y0, y1]), y_full) < tol, (tag, rel(torch.cat([y0, y1]), y_full))
@@ -119,7 +132,7 @@ def test_fused_block_syncbn_two_ranks_equals_full_batch(split):
                 assert rel(b0[name], b_full[name]) < tol and torch.equal(b0[name], b1[name]), (tag, name)
     # the BN parameter gradients are the point of the test: tight comparison fused vs torch.nn.SyncBatchNorm per rank
     for r_ in (0, 1):
-        gf, gm = got[r_][True][2], got[r_][False][2]
+        gf, gm = _pt(got[r_][True])[2], _pt(got[r_][False])[2]
         for name in gf:
             if ".bn." in name:
                 assert rel(gf[name], gm[name]) < 6e-2, (r_, name, rel(gf[name], gm[name]))
