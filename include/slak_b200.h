@@ -183,15 +183,26 @@ SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, 
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
 
 /* ---------------------------------------------------------------------------
- * Pointwise MLP of a Block on the tensor cores (models/SLaK.py:157-160, pwconv1 -> GELU -> pwconv2) with the
- * elementwise passes folded into the GEMM epilogues.  ROUND-2 DRAFT: exported and compiled, not yet validated on
- * hardware and not used unless SLAK_FUSED_MLP=1 (slak_b200/block.py); the default path keeps cuBLAS.
- *   fc1_gelu_fwd : h[M,N] = x[M,K] w[N,K]^T + bias (bf16), a = gelu(h)   -- nn.Linear + nn.GELU under autocast
- *   fc2_dgelu_bwd: dh[M,N] = (g[M,K] wt[N,K]^T) * gelu'(h); colpart[slak_mlp_parts(M,N)][N] fp32 = per-CTA partial
- *                  column sums of dh (fold with slak_colsum_f32: the bias gradient of pwconv1).  wt = W2^T.
- * All matrices bf16 row-major, 16-byte aligned; N % 128 == 0, K % 8 == 0, N <= 4096.
+ * Pointwise MLP of a Block on the tensor cores (models/SLaK.py:157-160, pwconv1 -> GELU -> pwconv2, and its backward):
+ * tcgen05 GEMMs with the elementwise passes folded into the epilogues (csrc/mlp_tc.cu).  All matrices bf16 row-major,
+ * 16-byte aligned, N % 8 == 0, K % 8 == 0, N <= 3072.
+ *   slak_mlp_gemm_nt(epi, ...): D[M,N] = a[M,K] b[N,K]^T, fp32 accumulate, then
+ *     epi 0 FC1   : out0 (may be NULL) = H = D + bias (bf16, nn.Linear under autocast), out1 = gelu(H) (exact erf GELU
+ *                   of the rounded H, nn.GELU on the bf16 tensor)
+ *     epi 1 BIAS  : out0 = D + bias
+ *     epi 2 DGELU : out0 = dH = D * gelu'(aux_h); colpart[slak_mlp_parts(M,N)][N] fp32 = per-CTA partial column sums of
+ *                   dH (fold with slak_colsum_f32: the bias gradient of pwconv1)
+ *     epi 3 PLAIN : out0 = D
+ *   slak_mlp_gemm_tn_splitk: part[slak_mlp_wgrad_splits(M,Ma,Nb)][Ma][Nb] fp32 = per-split partial sums of
+ *     p[M,Ma]^T q[M,Nb] (contraction over the M tokens: the weight gradients dW = dY^T X that autograd forms for
+ *     nn.Linear); fold with slak_colsum_f32(part, splits, Ma*Nb, dW): fixed order, deterministic.
+ *   slak_mlp_fc1_gelu_fwd / slak_mlp_fc2_dgelu_bwd: the epi 0 / epi 2 calls under their round-1 names.
  * ------------------------------------------------------------------------- */
 SLAK_API int slak_mlp_parts(int M, int N);
+SLAK_API int slak_mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const void* aux_h, void* out0,
+                              void* out1, float* colpart, int M, int N, int K, void* stream);
+SLAK_API int slak_mlp_wgrad_splits(int M, int Ma, int Nb);
+SLAK_API int slak_mlp_gemm_tn_splitk(const void* p, const void* q, float* part, int M, int Ma, int Nb, void* stream);
 SLAK_API int slak_mlp_fc1_gelu_fwd(const void* x, const void* w, const float* bias, void* h, void* a, int M, int N,
                                    int K, void* stream);
 SLAK_API int slak_mlp_fc2_dgelu_bwd(const void* g, const void* wt, const void* h, void* dh, float* colpart, int M,

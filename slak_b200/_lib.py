@@ -53,6 +53,9 @@ SIGNATURES = {
     "slak_bn3_finalize_bwd": (_i, [_vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "slak_bn3_bwd_apply": (_i, [_vp] * 8 + [_i] * 3 + [_vp]),
     "slak_mlp_parts": (_i, [_i, _i]),
+    "slak_mlp_gemm_nt": (_i, [_i] + [_vp] * 7 + [_i] * 3 + [_vp]),
+    "slak_mlp_wgrad_splits": (_i, [_i] * 3),
+    "slak_mlp_gemm_tn_splitk": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
     "slak_mlp_fc1_gelu_fwd": (_i, [_vp] * 5 + [_i] * 3 + [_vp]),
     "slak_mlp_fc2_dgelu_bwd": (_i, [_vp] * 5 + [_i] * 3 + [_vp]),
     "slak_colsum_f32": (_i, [_vp, _i, _i, _vp, _vp]),

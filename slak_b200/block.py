@@ -37,12 +37,33 @@ def _ck(rc, what):
     _lib.check(rc, what)
 
 
-# round-2 draft of the tcgen05 pointwise MLP (csrc/mlp_tc.cu): opt-in until it has been validated on hardware
-FUSED_MLP = os.environ.get("SLAK_FUSED_MLP", "0") == "1"
+# the pointwise MLP runs on this library's tcgen05 GEMMs (csrc/mlp_tc.cu); SLAK_FUSED_MLP=0 routes it through
+# torch.mm (cuBLAS) + the separate GELU passes instead (also taken for widths the kernels do not cover)
+FUSED_MLP = os.environ.get("SLAK_FUSED_MLP", "1") == "1"
+EPI_FC1, EPI_BIAS, EPI_DGELU, EPI_PLAIN = 0, 1, 2, 3
 
 
-def _fused_mlp_ok(M, N, K):
-    return N % 128 == 0 and K % 8 == 0 and N <= 4096 and M > 0
+def _fused_mlp_ok(M, C):
+    """Shapes the tcgen05 MLP kernels take: 16-byte rows for the tensor maps, hidden width within the DGELU epilogue's
+    shared-memory column accumulators."""
+    return M > 0 and C % 8 == 0 and 4 * C <= 3072
+
+
+def _gemm_nt(lib, st, epi, a, b, bias, aux_h, out0, out1, colpart, M, N, K):
+    _ck(lib.slak_mlp_gemm_nt(epi, _p(a), _p(b), _p(bias), _p(aux_h), _p(out0), _p(out1), _p(colpart), M, N, K, st),
+        "slak_mlp_gemm_nt")
+    ops._count(1)
+
+
+def _wgrad(lib, st, p, q, M, Ma, Nb):
+    """dW[Ma, Nb] = p[M, Ma]^T q[M, Nb] (fp32): split-K tcgen05 GEMM over the tokens + fixed-order fold."""
+    splits = lib.slak_mlp_wgrad_splits(M, Ma, Nb)
+    part = torch.empty((splits, Ma * Nb), dtype=torch.float32, device=p.device)
+    _ck(lib.slak_mlp_gemm_tn_splitk(_p(p), _p(q), _p(part), M, Ma, Nb, st), "slak_mlp_gemm_tn_splitk")
+    ops._count(1)
+    if splits == 1:
+        return part.view(Ma, Nb)
+    return _colsum(lib, part, st).view(Ma, Nb)
 
 
 def _colsum(lib, part2d, st):
@@ -126,25 +147,30 @@ class FusedBlockFunction(torch.autograd.Function):
         rstd = torch.empty((N * HW,), dtype=torch.float32, device=dev)
         _ck(lib.slak_bn3_sum_ln_fwd(_p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(lnb), cfg["ln_eps"],
                                     _p(xn), _p(mu), _p(rstd), N, C, HW, st), "slak_bn3_sum_ln_fwd")
-        # pointwise MLP (cuBLAS): bf16 operands, fp32 accumulate
+        # pointwise MLP: bf16 operands, fp32 accumulate
         W1b, W2b = W1.to(bf16), W2.to(bf16)
-        xf = xn.view(N * HW, C)
-        if FUSED_MLP and _fused_mlp_ok(N * HW, W1b.shape[0], C):
-            # round-2 draft (csrc/mlp_tc.cu): GEMM1 + bias + GELU in one tcgen05 kernel, H and A written once
-            h = torch.empty((N * HW, W1b.shape[0]), dtype=bf16, device=dev)
-            a = torch.empty_like(h)
-            _ck(lib.slak_mlp_fc1_gelu_fwd(_p(xf), _p(W1b), _p(b1.float().contiguous()), _p(h), _p(a), N * HW,
-                                          W1b.shape[0], C, st), "slak_mlp_fc1_gelu_fwd")
-            ops._count(1)
-        else:
-            h = torch.addmm(b1.to(bf16), xf, W1b.t())
-            a = F.gelu(h)
-        h2 = torch.addmm(b2.to(bf16), a, W2b.t())
+        M = N * HW
+        xf = xn.view(M, C)
+        fused_mlp = FUSED_MLP and _fused_mlp_ok(M, C)
+        with ops.timed("mlp_fwd", (M, C)):
+            if fused_mlp:
+                # tcgen05 GEMMs (csrc/mlp_tc.cu): pwconv1 + bias + GELU in one kernel (H and A written once, H only
+                # when a backward follows), pwconv2 + bias in the second
+                h = torch.empty((M, 4 * C), dtype=bf16, device=dev) if training else None
+                a = torch.empty((M, 4 * C), dtype=bf16, device=dev)
+                _gemm_nt(lib, st, EPI_FC1, xf, W1b, b1.float().contiguous(), None, h, a, None, M, 4 * C, C)
+                h2 = torch.empty((M, C), dtype=bf16, device=dev)
+                _gemm_nt(lib, st, EPI_BIAS, a, W2b, b2.float().contiguous(), None, h2, None, None, M, C, 4 * C)
+            else:
+                h = torch.addmm(b1.to(bf16), xf, W1b.t())
+                a = F.gelu(h)
+                h2 = torch.addmm(b2.to(bf16), a, W2b.t())
         out = torch.empty_like(x)
         _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), None, N, C, HW, st),
             "slak_block_residual_fwd")
         ops._count(2)
         ctx.cfg = cfg
+        ctx.fused_mlp = fused_mlp
         ctx.count = count
         ctx.count_dev = count_dev
         ctx.dims = (N, C, H, W, KL)
@@ -181,29 +207,37 @@ class FusedBlockFunction(torch.autograd.Function):
             "slak_block_residual_bwd")
         dg2 = _colsum(lib, dgp.view(parts, 2 * C), st).view(2, C)
         dgamma, db2 = dg2[0], dg2[1]
-        # ---- MLP backward (cuBLAS GEMMs + one fused GELU'/bias-gradient pass) -----------------------------
-        dW2 = torch.mm(dh2.t(), a).float()
+        # ---- MLP backward ---------------------------------------------------------------------------------
         K = h.shape[1]
-        if FUSED_MLP and _fused_mlp_ok(N * HW, K, C):
-            # round-2 draft: dH = (dH2 W2) * gelu'(H) and the bias-gradient partials in the GEMM epilogue
-            parts = lib.slak_mlp_parts(N * HW, K)
-            hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
-            dh = torch.empty_like(h)
-            W2t = W2b.t().contiguous()                 # [4C, C]: K-major B operand
-            _ck(lib.slak_mlp_fc2_dgelu_bwd(_p(dh2), _p(W2t), _p(h), _p(dh), _p(hp), N * HW, K, C, st),
-                "slak_mlp_fc2_dgelu_bwd")
-            ops._count(1)
-        else:
-            da = torch.mm(dh2, W2b)
-            parts = lib.slak_gelu_bwd_bias_parts(N * HW, K)
-            hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
-            _ck(lib.slak_gelu_bwd_bias(_p(da), _p(h), _p(da), _p(hp), N * HW, K, st), "slak_gelu_bwd_bias")   # in place
-            dh = da
-            del da
-        db1 = _colsum(lib, hp, st)
-        xf = xn.view(N * HW, C)
-        dW1 = torch.mm(dh.t(), xf).float()
-        dxn = torch.mm(dh, W1b)
+        M = N * HW
+        xf = xn.view(M, C)
+        with ops.timed("mlp_bwd", (M, C)):
+            if ctx.fused_mlp:
+                # tcgen05 GEMMs (csrc/mlp_tc.cu): dH = (dH2 W2) * gelu'(H) with the bias-gradient partials in the
+                # epilogue (dA never reaches HBM), dXn = dH W1, and the two weight gradients as split-K GEMMs over
+                # the tokens with a fixed-order fold
+                W2t = W2b.t().contiguous()                 # [4C, C]: K-major B operand of dH2 W2
+                W1t = W1b.t().contiguous()                 # [C, 4C]: K-major B operand of dH W1
+                parts = lib.slak_mlp_parts(M, K)
+                hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
+                dh = torch.empty_like(h)
+                _gemm_nt(lib, st, EPI_DGELU, dh2, W2t, None, h, dh, None, hp, M, K, C)
+                db1 = _colsum(lib, hp, st)
+                dW2 = _wgrad(lib, st, dh2, a, M, C, K)
+                dW1 = _wgrad(lib, st, dh, xf, M, K, C)
+                dxn = torch.empty((M, C), dtype=bf16, device=dev)
+                _gemm_nt(lib, st, EPI_PLAIN, dh, W1t, None, None, dxn, None, None, M, C, K)
+            else:
+                dW2 = torch.mm(dh2.t(), a).float()
+                da = torch.mm(dh2, W2b)
+                parts = lib.slak_gelu_bwd_bias_parts(M, K)
+                hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
+                _ck(lib.slak_gelu_bwd_bias(_p(da), _p(h), _p(da), _p(hp), M, K, st), "slak_gelu_bwd_bias")   # in place
+                dh = da
+                del da
+                db1 = _colsum(lib, hp, st)
+                dW1 = torch.mm(dh.t(), xf).float()
+                dxn = torch.mm(dh, W1b)
         del dh
         # ---- LayerNorm backward + BatchNorm reductions ------------------------------------------------
         parts = lib.slak_bn3_sum_ln_bwd_parts(N, C, HW)

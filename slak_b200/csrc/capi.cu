@@ -31,9 +31,10 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
                const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
                cudaStream_t st);
 int mlp_parts(int M, int N);
-int mlp_fc1_gelu_fwd(const void* x, const void* w, const float* bias, void* h, void* a, int M, int N, int K, cudaStream_t st);
-int mlp_fc2_dgelu_bwd(const void* g, const void* wt, const void* h, void* dh, float* colpart, int M, int N, int K,
-                      cudaStream_t st);
+int mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const void* aux_h, void* out0, void* out1,
+                float* colpart, int M, int N, int K, cudaStream_t st);
+int mlp_wgrad_splits(int M, int Ma, int Nb);
+int mlp_gemm_tn_splitk(const void* p, const void* q, float* part, int M, int Ma, int Nb, cudaStream_t st);
 size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL);
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
@@ -356,22 +357,38 @@ SLAK_API int slak_colsum_f32(const float* part, int rows, int cols, float* out, 
   return blk::colsum(part, rows, cols, out, (cudaStream_t)stream);
 }
 
-// ---- pointwise MLP GEMMs with fused epilogues (round-2 draft, see csrc/mlp_tc.cu) ------------------
+// ---- pointwise MLP GEMMs with fused epilogues (csrc/mlp_tc.cu) -----------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 SLAK_API int slak_mlp_parts(int M, int N) { return tc::mlp_parts(M, N); }
+
+SLAK_API int slak_mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const void* aux_h, void* out0,
+                              void* out1, float* colpart, int M, int N, int K, void* stream) {
+  SLAK_REQUIRE(epi >= 0 && epi <= 3, SLAK_ERR_BAD_ARG, "unknown epilogue %d", epi);
+  SLAK_REQUIRE(a && b, SLAK_ERR_BAD_ARG, "null operand");
+  SLAK_REQUIRE(aligned16(a) && aligned16(b) && aligned16(bias) && aligned16(aux_h) && aligned16(out0) && aligned16(out1),
+               SLAK_ERR_BAD_ARG, "operands must be 16-byte aligned");
+  if (epi == 0) SLAK_REQUIRE(bias && out1, SLAK_ERR_BAD_ARG, "FC1 needs bias and the activation output");
+  if (epi == 1) SLAK_REQUIRE(bias && out0, SLAK_ERR_BAD_ARG, "BIAS needs bias and an output");
+  if (epi == 2) SLAK_REQUIRE(aux_h && out0 && colpart, SLAK_ERR_BAD_ARG, "DGELU needs H, an output and the column partials");
+  if (epi == 3) SLAK_REQUIRE(out0, SLAK_ERR_BAD_ARG, "PLAIN needs an output");
+  return tc::mlp_gemm_nt(epi, a, b, bias, aux_h, out0, out1, colpart, M, N, K, (cudaStream_t)stream);
+}
 
 SLAK_API int slak_mlp_fc1_gelu_fwd(const void* x, const void* w, const float* bias, void* h, void* a, int M, int N, int K,
                                    void* stream) {
-  SLAK_REQUIRE(x && w && bias && h && a, SLAK_ERR_BAD_ARG, "null tensor pointer");
-  SLAK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(bias) |
-                 reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(a)) & 15) == 0, SLAK_ERR_BAD_ARG,
-               "operands must be 16-byte aligned");
-  return tc::mlp_fc1_gelu_fwd(x, w, bias, h, a, M, N, K, (cudaStream_t)stream);
+  return slak_mlp_gemm_nt(0, x, w, bias, nullptr, h, a, nullptr, M, N, K, stream);
 }
 
 SLAK_API int slak_mlp_fc2_dgelu_bwd(const void* g, const void* wt, const void* h, void* dh, float* colpart, int M, int N,
                                     int K, void* stream) {
-  SLAK_REQUIRE(g && wt && h && dh && colpart, SLAK_ERR_BAD_ARG, "null tensor pointer");
-  SLAK_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(wt) | reinterpret_cast<uintptr_t>(h) |
-                 reinterpret_cast<uintptr_t>(dh)) & 15) == 0, SLAK_ERR_BAD_ARG, "operands must be 16-byte aligned");
-  return tc::mlp_fc2_dgelu_bwd(g, wt, h, dh, colpart, M, N, K, (cudaStream_t)stream);
+  return slak_mlp_gemm_nt(2, g, wt, nullptr, h, dh, nullptr, colpart, M, N, K, stream);
+}
+
+SLAK_API int slak_mlp_wgrad_splits(int M, int Ma, int Nb) { return tc::mlp_wgrad_splits(M, Ma, Nb); }
+
+SLAK_API int slak_mlp_gemm_tn_splitk(const void* p, const void* q, float* part, int M, int Ma, int Nb, void* stream) {
+  SLAK_REQUIRE(p && q && part, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(aligned16(p) && aligned16(q) && aligned16(part), SLAK_ERR_BAD_ARG, "operands must be 16-byte aligned");
+  return tc::mlp_gemm_tn_splitk(p, q, part, M, Ma, Nb, (cudaStream_t)stream);
 }

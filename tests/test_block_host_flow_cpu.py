@@ -49,14 +49,15 @@ def test_forward_backward_and_eval_call_sequences(stubbed, monkeypatch, dim, fus
     assert y.shape == x.shape and y.dtype == torch.float32
     fwd = list(stubbed.calls)
     assert fwd[:4] == ["slak_block_conv_fwd_workspace", "slak_block_conv_fwd", "slak_bn3_finalize_fwd", "slak_bn3_sum_ln_fwd"]
-    assert ("slak_mlp_fc1_gelu_fwd" in fwd) == fused_mlp and fwd[-1] == "slak_block_residual_fwd"
+    assert ("slak_mlp_gemm_nt" in fwd) == fused_mlp and fwd[-1] == "slak_block_residual_fwd"
     del stubbed.calls[:]
     y.backward(torch.ones_like(y))
     bwd = list(stubbed.calls)
     for name in ("slak_block_residual_bwd", "slak_colsum_f32", "slak_bn3_sum_ln_bwd", "slak_bn3_finalize_bwd",
                  "slak_bn3_bwd_apply", "slak_lk_branches_bwd_data_f32", "slak_lk_branches_bwd_filter"):
         assert name in bwd, name
-    assert ("slak_mlp_fc2_dgelu_bwd" in bwd) == fused_mlp and ("slak_gelu_bwd_bias" in bwd) == (not fused_mlp)
+    assert ("slak_mlp_gemm_tn_splitk" in bwd) == fused_mlp and ("slak_gelu_bwd_bias" in bwd) == (not fused_mlp)
+    assert bwd.count("slak_mlp_gemm_nt") == (2 if fused_mlp else 0) and bwd.count("slak_mlp_gemm_tn_splitk") == (2 if fused_mlp else 0)
     # one gradient per parameter, with the parameter's shape and dtype
     assert x.grad.shape == x.shape
     for n, p in blk.named_parameters():
