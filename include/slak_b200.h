@@ -198,6 +198,9 @@ SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, 
  *     nn.Linear); fold with slak_colsum_f32(part, splits, Ma*Nb, dW): fixed order, deterministic.
  *   slak_mlp_fc1_gelu_fwd / slak_mlp_fc2_dgelu_bwd: the epi 0 / epi 2 calls under their round-1 names.
  * ------------------------------------------------------------------------- */
+/* fp32 weight [R][Cc] (an nn.Linear parameter) -> bf16 copy wb [R][Cc] and bf16 transpose wt [Cc][R] in one pass: the
+ * autocast cast of the weight plus the K-major operand of its data-gradient GEMM */
+SLAK_API int slak_cast_transpose_bf16(const float* w, void* wb, void* wt, int R, int Cc, void* stream);
 SLAK_API int slak_mlp_parts(int M, int N);
 SLAK_API int slak_mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const void* aux_h, void* out0,
                               void* out1, float* colpart, int M, int N, int K, void* stream);

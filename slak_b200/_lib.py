@@ -52,6 +52,7 @@ SIGNATURES = {
     "slak_bn3_sum_ln_bwd": (_i, [_vp] * 11 + [_i] * 3 + [_vp]),
     "slak_bn3_finalize_bwd": (_i, [_vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "slak_bn3_bwd_apply": (_i, [_vp] * 8 + [_i] * 3 + [_vp]),
+    "slak_cast_transpose_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "slak_mlp_parts": (_i, [_i, _i]),
     "slak_mlp_gemm_nt": (_i, [_i] + [_vp] * 7 + [_i] * 3 + [_vp]),
     "slak_mlp_wgrad_splits": (_i, [_i] * 3),

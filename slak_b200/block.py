@@ -148,10 +148,20 @@ class FusedBlockFunction(torch.autograd.Function):
         _ck(lib.slak_bn3_sum_ln_fwd(_p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(lnb), cfg["ln_eps"],
                                     _p(xn), _p(mu), _p(rstd), N, C, HW, st), "slak_bn3_sum_ln_fwd")
         # pointwise MLP: bf16 operands, fp32 accumulate
-        W1b, W2b = W1.to(bf16), W2.to(bf16)
         M = N * HW
         xf = xn.view(M, C)
         fused_mlp = FUSED_MLP and _fused_mlp_ok(M, C)
+        W1t = W2t = None
+        if fused_mlp and training and W1.dtype == torch.float32 and W1.is_contiguous() and W2.is_contiguous():
+            # autocast's bf16 copies of the two weights and, in the same pass, their transposes (the K-major operands of
+            # the data-gradient GEMMs in backward)
+            W1b, W1t = torch.empty((4 * C, C), dtype=bf16, device=dev), torch.empty((C, 4 * C), dtype=bf16, device=dev)
+            W2b, W2t = torch.empty((C, 4 * C), dtype=bf16, device=dev), torch.empty((4 * C, C), dtype=bf16, device=dev)
+            _ck(lib.slak_cast_transpose_bf16(_p(W1), _p(W1b), _p(W1t), 4 * C, C, st), "slak_cast_transpose_bf16")
+            _ck(lib.slak_cast_transpose_bf16(_p(W2), _p(W2b), _p(W2t), C, 4 * C, st), "slak_cast_transpose_bf16")
+            ops._count(2)
+        else:
+            W1b, W2b = W1.to(bf16), W2.to(bf16)
         with ops.timed("mlp_fwd", (M, C)):
             if fused_mlp:
                 # tcgen05 GEMMs (csrc/mlp_tc.cu): pwconv1 + bias + GELU in one kernel (H and A written once, H only
@@ -175,7 +185,7 @@ class FusedBlockFunction(torch.autograd.Function):
         ctx.count_dev = count_dev
         ctx.dims = (N, C, H, W, KL)
         ctx.save_for_backward(xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd,
-                              xn, h, a, h2, W1b, W2b, gamma, dp)
+                              xn, h, a, h2, W1b, W2b, gamma, dp, W1t, W2t)
         return out
 
     @staticmethod
@@ -186,7 +196,7 @@ class FusedBlockFunction(torch.autograd.Function):
     @staticmethod
     def _backward(ctx, dout):
         (xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd, xn, h, a, h2, W1b, W2b,
-         gamma, dp) = ctx.saved_tensors
+         gamma, dp, W1t, W2t) = ctx.saved_tensors
         cfg = ctx.cfg
         if not cfg["training"]:
             raise RuntimeError("FusedBlockFunction.backward is only defined for training-mode BatchNorm")
@@ -216,8 +226,9 @@ class FusedBlockFunction(torch.autograd.Function):
                 # tcgen05 GEMMs (csrc/mlp_tc.cu): dH = (dH2 W2) * gelu'(H) with the bias-gradient partials in the
                 # epilogue (dA never reaches HBM), dXn = dH W1, and the two weight gradients as split-K GEMMs over
                 # the tokens with a fixed-order fold
-                W2t = W2b.t().contiguous()                 # [4C, C]: K-major B operand of dH2 W2
-                W1t = W1b.t().contiguous()                 # [C, 4C]: K-major B operand of dH W1
+                if W2t is None:
+                    W2t = W2b.t().contiguous()             # [4C, C]: K-major B operand of dH2 W2
+                    W1t = W1b.t().contiguous()             # [C, 4C]: K-major B operand of dH W1
                 parts = lib.slak_mlp_parts(M, K)
                 hp = torch.empty((parts, K), dtype=torch.float32, device=dev)
                 dh = torch.empty_like(h)

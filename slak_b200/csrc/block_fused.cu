@@ -656,7 +656,58 @@ colsum_kernel(const float* __restrict__ part, int rows, int cols, float* __restr
 }
 
 // ---- host launchers -------------------------------------------------------------------------
+// few rows x very many columns (split-K partials of a weight gradient): one thread per 4 columns, rows added in order
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const float4* __restrict__ part, int rows, int cols4,
+                                                          float4* __restrict__ out) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols4; c += gridDim.x * blockDim.x) {
+    float4 a = part[c];
+    for (int r = 1; r < rows; ++r) {
+      const float4 b = part[(size_t)r * cols4 + c];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[c] = a;
+  }
+}
+// fp32 [R][Cc] -> bf16 [R][Cc] and bf16 [Cc][R] in one pass (the two operand layouts of an nn.Linear weight: forward
+// and data-gradient GEMMs both want their contraction axis contiguous); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
+                                                             __nv_bfloat16* __restrict__ wt, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < Cc) {
+      v = w[(size_t)r * Cc + c];
+      wb[(size_t)r * Cc + c] = __float2bfloat16_rn(v);
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (r < R && c < Cc) wt[(size_t)c * R + r] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+  }
+}
+int cast_transpose(const float* w, void* wb, void* wt, int R, int Cc, cudaStream_t st) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32);
+  cast_transpose_kernel<<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)wb, (__nv_bfloat16*)wt, R, Cc);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
 int colsum(const float* part, int rows, int cols, float* out, cudaStream_t st) {
+  if (rows <= 16 && cols >= 16384 && cols % 4 == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int cols4 = cols / 4;
+    int grid = (cols4 + 255) / 256;
+    if (grid > 8 * sm_count()) grid = 8 * sm_count();
+    colsum_wide_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(part), rows, cols4, reinterpret_cast<float4*>(out));
+    SLAK_CUDA_TRY(cudaGetLastError());
+    return SLAK_OK;
+  }
   colsum_kernel<<<(cols + kCsCols - 1) / kCsCols, kCsCols * kCsGroups, 0, st>>>(part, rows, cols, out);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;

@@ -42,6 +42,7 @@ int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy
 // block_fused.cu
 namespace blk {
 int colsum(const float* part, int rows, int cols, float* out, cudaStream_t st);
+int cast_transpose(const float* w, void* wb, void* wt, int R, int Cc, cudaStream_t st);
 int bn3_stats_finalize(const float* part, int splits, double* sums_ws, int C, cudaStream_t st);
 int bn3_finalize_fwd(const double* sums, double count, const double* count_dev, const float* const* bnw, const float* const* bnb,
                      float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale, float* shift,
@@ -355,6 +356,11 @@ SLAK_API int slak_layernorm2d_bwd(const void* g, int g_dtype, const void* x, int
 SLAK_API int slak_colsum_f32(const float* part, int rows, int cols, float* out, void* stream) {
   SLAK_REQUIRE(part && out && rows > 0 && cols > 0, SLAK_ERR_BAD_ARG, "bad argument");
   return blk::colsum(part, rows, cols, out, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_cast_transpose_bf16(const float* w, void* wb, void* wt, int R, int Cc, void* stream) {
+  SLAK_REQUIRE(w && wb && wt && R > 0 && Cc > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::cast_transpose(w, wb, wt, R, Cc, (cudaStream_t)stream);
 }
 
 // ---- pointwise MLP GEMMs with fused epilogues (csrc/mlp_tc.cu) -----------------------------------------

@@ -56,13 +56,53 @@ struct Params {
   int write_h;                      // FC1: also store H (training); 0 = only A (inference)
 };
 
-// d/dx [x Phi(x)] and x Phi(x) with Phi through erf's rational approximation (A&S 7.1.26, |err| <= 1.5e-7)
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float e = __expf(-0.5f * x * x);
-  const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  cdf = 0.5f + copysignf(0.5f * fmaf(-poly, e, 1.f), x);
-  pdf = 0.39894228040143268f * e;
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction on sm_100a) -------------------------
+// The GELU epilogues are bound by instruction issue (each element costs ~25 scalar instructions in the A&S 7.1.26
+// form, and its exp / rcp and the fp32 -> bf16 -> fp32 round trips go through the quarter-rate XU pipe); in packed
+// form with a polynomial Phi they cost ~10.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 mk2u(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void un2(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 splat(float c) { return mk2(c, c); }
+// (lo, hi) -> bf16x2 bits (round to nearest even), and back (exact)
+__device__ __forceinline__ uint32_t pack2(f2 a) { float lo, hi; un2(a, lo, hi); return pack_bf16(lo, hi); }
+__device__ __forceinline__ f2 unpack2(uint32_t b) { return mk2u(b << 16, b & 0xffff0000u); }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+// Phi(x) = (1 + erf(x / sqrt 2)) / 2 for a pair: Phi = sat(0.5 + x Q(x^2)), Q the degree-8 near-minimax polynomial of
+// (Phi(x) - 0.5) / x on [-4.25, 4.25] (odd Chebyshev fit).  Beyond the interval the leading term (positive) drives
+// 0.5 + x Q to +-infinity and the saturation gives exactly 1 / 0.  |error| <= 1.1e-5 over the whole real line in fp32
+// Horner form (tools/gelu_poly.py), i.e. <= 1e-5 |x| in gelu(x) = x Phi(x): far below the bf16 rounding of the result.
+__device__ __forceinline__ f2 phi2(f2 x, f2 u) {
+  f2 q = splat(5.342467094e-11f);
+  q = fma2(q, u, splat(-5.157194671e-09f));
+  q = fma2(q, u, splat(2.201571192e-07f));
+  q = fma2(q, u, splat(-5.536209756e-06f));
+  q = fma2(q, u, splat(9.255817713e-05f));
+  q = fma2(q, u, splat(-1.103906194e-03f));
+  q = fma2(q, u, splat(9.802624583e-03f));
+  q = fma2(q, u, splat(-6.632731855e-02f));
+  q = fma2(q, u, splat(3.988958895e-01f));
+  float x0, x1, q0, q1;
+  un2(x, x0, x1);
+  un2(q, q0, q1);
+  return mk2(fma_sat(x0, q0, 0.5f), fma_sat(x1, q1, 0.5f));
+}
+// gelu(x) = x Phi(x)
+__device__ __forceinline__ f2 gelu2(f2 x) { return mul2(x, phi2(x, mul2(x, x))); }
+// gelu'(x) = Phi(x) + x phi(x), phi(x) = exp(-x^2 / 2) / sqrt(2 pi) through ex2.approx (one MUFU per element)
+__device__ __forceinline__ f2 dgelu2(f2 x) {
+  const f2 u = mul2(x, x);
+  const f2 P = phi2(x, u);
+  float e0, e1;
+  un2(mul2(u, splat(-0.72134752044448170f)), e0, e1);           // -x^2 / 2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e1));
+  return fma2(mul2(x, splat(0.39894228040143268f)), mk2(e0, e1), P);
 }
 
 template <int BN, int EPI>
@@ -158,11 +198,24 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     const uint32_t stg_s = base + C::kOffStg + g * 2 * kBox * 2;
     float* col = reinterpret_cast<float*>(sm + C::kOffCol);
     float* scratch = col + 3072;                          // [8 warps][64]
+    float* bias_s = col + g * 64;                         // FC1 / BIAS: the group's rounded bias slab (col[] is DGELU's)
     int it = 0, slab_ctr = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int m0 = (t / n_tiles) * BM, nt0 = (t % n_tiles) * BN;
       const int ab = it & 1, aph = (it >> 1) & 1;
       const int m = m0 + L;
+      if constexpr (EPI == EPI_DGELU) {
+        // pull this thread's H row segments of the CTA's NEXT tile into L2 (one 128-byte line per 64-column slab), so that
+        // the row-per-thread loads below see L2 latency instead of HBM latency
+        const int tn = t + gridDim.x;
+        if (tn < tiles) {
+          const int mn = (tn / n_tiles) * BM + L, nn = (tn % n_tiles) * BN + 64 * g * SPG;
+          if (mn < P.M)
+#pragma unroll
+            for (int q = 0; q < SPG; ++q)
+              if (nn + 64 * q < P.N) prefetch_l2(P.h + (size_t)mn * P.N + nn + 64 * q);
+        }
+      }
 #pragma unroll 1
       for (int sl = 0; sl < SPG; ++sl, ++slab_ctr) {
         const int n0 = nt0 + 64 * (g * SPG + sl);         // first column of the slab
@@ -191,84 +244,94 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));
         }
-        // staging: FC1 uses both slabs of the group (H, A) for one 64-column slab; the single-output epilogues
-        // alternate between them, so only the store issued two slabs ago has to have finished reading
+        // staging: the single-output epilogues alternate between the group's two slabs; FC1 writes H to slab 0 and A to
+        // slab 1 and stores them as separate bulk groups.  Either way a slab is rewritten one slab period after its
+        // store was issued, and only the store issued before the most recent one has to have finished reading.
         const int buf = (EPI == EPI_FC1) ? 0 : (slab_ctr & 1);
-        if (e == 0 && lane == 0) {
-          if (EPI == EPI_FC1) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
+        if (e == 0 && lane == 0) bulk_wait_group_read<1>();
+        if constexpr (EPI == EPI_FC1 || EPI == EPI_BIAS) {
+          // the slab's 64 bias values, rounded to bf16 once (b.to(bf16) of the module path), for broadcast reads below;
+          // the previous slab's readers are past the barrier that closed it
+          if (e == 1 || e == 2) {
+            const int c = (e - 1) * 32 + lane;
+            bias_s[c] = (n0 + c < P.N) ? __bfloat162float(__float2bfloat16_rn(__ldg(P.bias + n0 + c))) : 0.f;
+          }
         }
         named_bar_sync(nb, 128);
         uint8_t* s0 = stg + buf * 2 * kBox;
         uint8_t* s1 = stg + 2 * kBox;
-        float cs[(EPI == EPI_DGELU) ? 64 : 1];
+        if constexpr (EPI == EPI_FC1) {
+          // pass 1: H = acc + bias, rounded once; its store drains while pass 2 computes the GELU
+          uint32_t hb[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float o[8], a[8];
-          if constexpr (EPI == EPI_FC1 || EPI == EPI_BIAS) {
-            float bb[8];
-            if (n0 + 8 * j < P.N) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + 8 * j));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + 8 * j + 4));
-              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * j);          // bf16-rounded bias, broadcast reads
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * j + 4);
+            const f2 bb[4] = {mk2(b0.x, b0.y), mk2(b0.z, b0.w), mk2(b1.x, b1.y), mk2(b1.z, b1.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hb[4 * j + k] = pack2(add2(mk2u(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]), bb[k]));
+            if (P.write_h)
+              *reinterpret_cast<uint4*>(s0 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4)) =
+                  make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+          }
+          if (P.write_h) {
+            fence_proxy_async();
+            named_bar_sync(nb, 128);
+            if (e == 0 && lane == 0) {
+              tma_store_3d(&o0map, stg_s, n0, m0, 0);
+              tma_store_3d(&o0map, stg_s + kBox, n0, m0 + 64, 0);
+              bulk_commit_group();
+              bulk_wait_group_read<1>();                 // the previous slab's A store (older than the H store just issued)
+            }
+          } else if (e == 0 && lane == 0) {
+            bulk_wait_group_read<0>();
+          }
+          // pass 2: A = gelu(H) of the value that is stored
+          uint32_t ab[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ab[i] = pack2(gelu2(unpack2(hb[i])));
+          named_bar_sync(nb, 128);                       // slab 1 is free (the elected thread's wait above)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(s1 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4)) =
+                make_uint4(ab[4 * j], ab[4 * j + 1], ab[4 * j + 2], ab[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t ob[4];
+            if constexpr (EPI == EPI_BIAS) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * j + 4);
+              const f2 bb[4] = {mk2(b0.x, b0.y), mk2(b0.z, b0.w), mk2(b1.x, b1.y), mk2(b1.z, b1.w)};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ob[k] = pack2(add2(mk2u(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]), bb[k]));
+            } else if constexpr (EPI == EPI_DGELU) {
+              const uint32_t hb[4] = {hraw[j].x, hraw[j].y, hraw[j].z, hraw[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ob[k] = pack2(mul2(mk2u(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]), dgelu2(unpack2(hb[k]))));
+              if (m >= P.M) { ob[0] = ob[1] = ob[2] = ob[3] = 0u; }          // rows beyond M must not reach the column sums
             } else {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) bb[k] = 0.f;
+              for (int k = 0; k < 4; ++k) ob[k] = pack_bf16(__uint_as_float(v[8 * j + 2 * k]), __uint_as_float(v[8 * j + 2 * k + 1]));
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float hv = __uint_as_float(v[8 * j + k]) + __bfloat162float(__float2bfloat16_rn(bb[k]));
-              o[k] = hv;
-              if constexpr (EPI == EPI_FC1) {
-                const float hr = __bfloat162float(__float2bfloat16_rn(hv));     // GELU of the value that is stored
-                float cdf, pdf;
-                gelu_parts(hr, cdf, pdf);
-                a[k] = hr * cdf;
-              }
-            }
-          } else if constexpr (EPI == EPI_DGELU) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hraw[j]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 hx = __bfloat1622float2(h2[k]);
-              float c0, p0, c1, p1;
-              gelu_parts(hx.x, c0, p0);
-              gelu_parts(hx.y, c1, p1);
-              o[2 * k] = __uint_as_float(v[8 * j + 2 * k]) * fmaf(hx.x, p0, c0);
-              o[2 * k + 1] = __uint_as_float(v[8 * j + 2 * k + 1]) * fmaf(hx.y, p1, c1);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              cs[8 * j + k] = (m < P.M) ? __bfloat162float(__float2bfloat16_rn(o[k])) : 0.f;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v[8 * j + k]);
+            *reinterpret_cast<uint4*>(s0 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4)) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
           }
-          const uint32_t off = (uint32_t)L * 128 + ((j ^ (L & 7)) << 4);
-          if (EPI != EPI_FC1 || P.write_h)
-            *reinterpret_cast<uint4*>(s0 + off) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
-                                                             pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-          if constexpr (EPI == EPI_FC1)
-            *reinterpret_cast<uint4*>(s1 + off) = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
-                                                             pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+        }
+        if constexpr (EPI == EPI_DGELU) {
+          // column sums of the STORED (rounded) dH: warp e wrote rows 32 e .. 32 e + 31 of the slab itself, lane l now adds
+          // up columns 2l, 2l + 1 over them (one conflict-free 128-byte row per load instruction)
+          __syncwarp();
+          f2 acc2 = splat(0.f);
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t row = (uint32_t)(e * 32 + r);
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(s0 + row * 128 + ((((uint32_t)lane >> 2) ^ (row & 7)) << 4) + (lane & 3) * 4);
+            acc2 = add2(acc2, unpack2(w));
+          }
+          *reinterpret_cast<f2*>(scratch + (warp - 4) * 64 + 2 * lane) = acc2;
         }
         fence_proxy_async();
-        if constexpr (EPI == EPI_DGELU) {
-          // column sums over the warp's 32 rows by a transposing butterfly (lane l ends with column l / 32 + l)
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float* c = cs + 32 * hh;
-#pragma unroll
-            for (int o2 = 16; o2 >= 1; o2 >>= 1) {
-              const bool up = (lane & o2) != 0;
-#pragma unroll
-              for (int k = 0; k < o2; ++k) {
-                const float send = up ? c[k] : c[k + o2], keep = up ? c[k + o2] : c[k];
-                c[k] = keep + __shfl_xor_sync(0xffffffffu, send, o2);
-              }
-            }
-            scratch[(warp - 4) * 64 + 32 * hh + lane] = c[0];
-          }
-        }
         named_bar_sync(nb, 128);
         if (EPI == EPI_DGELU && e == 0) {      // one warp folds the group's four row blocks into the CTA's column accumulators
 #pragma unroll
@@ -281,18 +344,16 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
           }
         }
         if (e == 0 && lane == 0) {
-          const uint32_t a0 = stg_s + buf * 2 * kBox;
-          if (EPI != EPI_FC1 || P.write_h) {
+          if constexpr (EPI == EPI_FC1) {
+            tma_store_3d(&o1map, stg_s + 2 * kBox, n0, m0, 0);
+            tma_store_3d(&o1map, stg_s + 2 * kBox + kBox, n0, m0 + 64, 0);
+          } else {
+            const uint32_t a0 = stg_s + buf * 2 * kBox;
             tma_store_3d(&o0map, a0, n0, m0, 0);
             tma_store_3d(&o0map, a0 + kBox, n0, m0 + 64, 0);
           }
-          if (EPI == EPI_FC1) {
-            tma_store_3d(&o1map, stg_s + 2 * kBox, n0, m0, 0);
-            tma_store_3d(&o1map, stg_s + 2 * kBox + kBox, n0, m0 + 64, 0);
-          }
           bulk_commit_group();
         }
-        if (EPI == EPI_DGELU) named_bar_sync(nb, 128);    // scratch is rewritten by the next slab
       }
     }
     if (e == 0 && lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last tile store
@@ -497,7 +558,7 @@ static void wg_plan(int M, int Ma, int Nb, int* BN, int* tiles_a, int* tiles_b, 
   *tiles_a = (Ma + 127) / 128;
   *tiles_b = (Nb + *BN - 1) / *BN;
   const int tiles = *tiles_a * *tiles_b;
-  int s = (sm_count() + tiles - 1) / tiles;               // about one wave of CTAs
+  int s = sm_count() / tiles;                             // at most one wave of CTAs (a second, partial wave costs a full pass)
   const int kblocks = (M + 63) / 64;
   if (s > kblocks) s = kblocks;
   if (s < 1) s = 1;

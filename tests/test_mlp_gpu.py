@@ -139,3 +139,22 @@ def test_fused_block_tcgen05_mlp_equals_cublas_route(dim, hw):
     assert rel(dx0, dx1) < 1e-2, rel(dx0, dx1)
     for k in g0:
         assert rel(g0[k], g1[k]) < 1e-2, (k, rel(g0[k], g1[k]))
+
+
+def test_cast_transpose_and_wide_fold():
+    L, lib = _lib()
+    for R, Cc in [(384, 96), (96, 384), (3072, 768), (40, 8), (33, 17)]:
+        w = torch.randn(R, Cc, device=DEV)
+        wb = torch.empty(R, Cc, dtype=torch.bfloat16, device=DEV)
+        wt = torch.empty(Cc, R, dtype=torch.bfloat16, device=DEV)
+        L.check(lib.slak_cast_transpose_bf16(w.data_ptr(), wb.data_ptr(), wt.data_ptr(), R, Cc, L.current_stream_ptr()), "ct")
+        assert torch.equal(wb, w.bfloat16()) and torch.equal(wt, w.bfloat16().t().contiguous())
+    # split-K partial fold over few rows / very many columns (the weight-gradient partials)
+    for rows, cols in [(2, 768 * 3072), (8, 384 * 1536), (1, 16384), (3, 20000)]:
+        part = torch.randn(rows, cols, device=DEV)
+        out = torch.empty(cols, device=DEV)
+        L.check(lib.slak_colsum_f32(part.data_ptr(), rows, cols, out.data_ptr(), L.current_stream_ptr()), "colsum")
+        ref = part[0].clone()
+        for r in range(1, rows):
+            ref += part[r]
+        assert torch.equal(out, ref)            # rows added in order: bitwise the sequential sum
