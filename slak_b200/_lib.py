@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslak_b200.so")
+# SLAK_B200_LIB: load another build of the same library (e.g. the -DSLAK_ROLE_PROFILE build of tools/role_profile.sh)
+LIB_PATH = os.environ.get("SLAK_B200_LIB") or os.path.join(_HERE, "libslak_b200.so")
 
 SLAK_F32, SLAK_F16, SLAK_BF16 = 0, 1, 2
 

@@ -30,7 +30,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
-#include <stdlib.h>
 
 // -DSLAK_ROLE_PROFILE: CTA 0 prints, per warp role, the cycles spent in its main loop and the part of them spent
 // waiting on mbarriers / named barriers (debug aid for finding the critical role; never defined in the product build)
@@ -699,22 +698,9 @@ static int launch_fwd(const CUtensorMap& map, const CUtensorMap* ymaps, FwdParam
   return SLAK_OK;
 }
 
-// dwconv_tc_fwd2.cu: second-generation small-plane path (units of IMG images x CHB consecutive channels)
-int fwd2_piece_bytes(int N, int C, int H, int W, int KL);
-int lk3_fwd_tc2_splits(int N, int C, int H, int W);
-int lk3_fwd_tc2(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3, int N, int C,
-                int H, int W, int KL, float* stats, cudaStream_t st);
-static bool g_fwd2_enabled = true;     // SLAK_TC_SMALL_V1=1 keeps the first-generation kernels (A/B measurements)
-static bool fwd2_on() {
-  static int init = 0;
-  if (!init) { const char* e = getenv("SLAK_TC_SMALL_V1"); g_fwd2_enabled = !(e && e[0] == '1'); init = 1; }
-  return g_fwd2_enabled;
-}
-
 int lk3_fwd_tc_splits(int N, int C, int H, int W) {
   const TcShape s = tc_shape(H, W);
   if (s.tile == 0) return 0;
-  if (fwd2_on() && fwd2_piece_bytes(N, C, H, W, 5)) return lk3_fwd_tc2_splits(N, C, H, W);
   return tc_plan(N, C, s.tile, (128 / s.tile) * (64 / s.tile)).splits * kEpiGroups;   // statistics slots per channel
 }
 
@@ -723,7 +709,6 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
   SLAK_REQUIRE(lk3_tc_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   SLAK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SLAK_ERR_BAD_ARG, "x must be 16-byte aligned");
   SLAK_REQUIRE((2 * KL * 5 + 25) * 4 <= 4096, SLAK_ERR_UNSUPPORTED, "kernel side %d too large", KL);
-  if (fwd2_on() && fwd2_piece_bytes(N, C, H, W, KL)) return lk3_fwd_tc2(x, w1, w2, w3, y1, y2, y3, N, C, H, W, KL, stats, st);
   const TcShape s = tc_shape(H, W);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
