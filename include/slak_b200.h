@@ -65,7 +65,11 @@ SLAK_API int slak_device_ok(void);
  *          dtype is a 16-bit type the weights are rounded to it before use
  *          (what autocast's cast_inputs does to the reference's FP16 path,
  *          depthwise_conv2d_implicit_gemm.py:35) and products accumulate in fp32.
- * ------------------------------------------------------------------------- */
+ * Route: bf16 activations with fp32 taps and one kernel side equal to 5 (K x 5, 5 x K, 5 x 5 -- every depthwise
+ * shape of a Decom SLaK Block) on planes up to 62 x 62 run on the tcgen05 banded-Toeplitz kernels
+ * (slak_dwconv2d_uses_tc() == 1); everything else -- fp32 (exact, the reference's allclose tolerance), fp16, square
+ * kernels, larger planes -- runs the CUDA-core kernels. */
+SLAK_API int slak_dwconv2d_uses_tc(int N, int C, int H, int W, int kh, int kw, int dtype, int wdtype);
 SLAK_API int slak_dwconv2d_fwd(const void* x, const void* w, void* y,
                                int N, int C, int H, int W, int kh, int kw,
                                int dtype, int wdtype, void* stream);
@@ -248,6 +252,21 @@ SLAK_API int slak_layernorm2d_bwd(const void* g, int g_dtype, const void* x, int
 SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs,
                              float* const* extra_ptrs, const int64_t* numels,
                              int count, int64_t max_numel, void* stream);
+
+/* Fused multi-tensor AdamW + mask apply + mask-aware EMA, one launch (optim_factory.py:149-150 torch.optim.AdamW;
+ * sparse_core.py:322-333 Masking.apply_mask; model_sema.py:67-91 ModelEma.update).  All tables are DEVICE arrays
+ * indexed by tensor: p, g, m (exp_avg), v (exp_avg_sq) fp32 tensors of numel[t] elements; mask / ema tables and their
+ * entries may be NULL; lr / wd per tensor (double).  Work is a flat list of nchunks chunks (chunk_tensor[c],
+ * chunk_off[c]) of at most chunk_elems elements.  step_dev: device counter of completed steps (this call computes
+ * step + 1 and then increments it: CUDA-graph replayable).  do_adam = 0 applies only the mask / EMA part (p is the
+ * weight to average).  Per-element arithmetic: fp32 in the operation order of torch's single-tensor AdamW
+ * (csrc/optim.cu). */
+SLAK_API int slak_adamw_mask_ema_step(float* const* p, const float* const* g, float* const* m, float* const* v,
+                                      const float* const* mask, float* const* ema, const int64_t* numel,
+                                      const double* lr, const double* wd, const int32_t* chunk_tensor,
+                                      const int64_t* chunk_off, int nchunks, int chunk_elems, double beta1,
+                                      double beta2, double eps, double ema_decay, int64_t* step_dev, int do_adam,
+                                      void* stream);
 
 /* Magnitude prune of one layer: zero the mask at the k smallest |w| positions
  * (ties broken by lower flat index first, like a stable ascending sort).

@@ -28,6 +28,7 @@ SIGNATURES = {
     "slak_version": (_i, []),
     "slak_last_error": (ctypes.c_char_p, []),
     "slak_device_ok": (_i, []),
+    "slak_dwconv2d_uses_tc": (_i, [_i] * 8),
     "slak_dwconv2d_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "slak_dwconv2d_bwd_data": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "slak_dwconv2d_bwd_filter_workspace": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "slak_layernorm2d_bwd_parts": (_i, [_i, _i]),
     "slak_layernorm2d_bwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "slak_mask_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "slak_adamw_mask_ema_step": (_i, [_vp] * 11 + [_i, _i] + [ctypes.c_double] * 4 + [_vp, _i, _vp]),
     "slak_mask_prune_workspace": (_sz, [_i64]),
     "slak_mask_prune_magnitude": (_i, [_vp, _vp, _i64, _i64, _vp, _sz, _vp]),
 }

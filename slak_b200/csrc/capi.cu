@@ -81,6 +81,12 @@ size_t mask_prune_workspace(int64_t n);
 int mask_prune_magnitude(const float* w, float* mask, int64_t n, int64_t k, void* workspace,
                          cudaStream_t st);
 
+// optim.cu
+int adamw_mask_ema(float* const* p, const float* const* g, float* const* m, float* const* v, const float* const* mask,
+                   float* const* ema, const int64_t* numel, const double* lr, const double* wd, const int32_t* chunk_tensor,
+                   const int64_t* chunk_off, int nchunks, int chunk_elems, double beta1, double beta2, double eps,
+                   double ema_decay, int64_t* step_dev, int do_adam, cudaStream_t st);
+
 static int check_conv_args(const void* a, const void* b, const void* c, int N, int C, int H, int W,
                            int kh, int kw, int dtype, int wdtype) {
   SLAK_REQUIRE(a && b && c, SLAK_ERR_BAD_ARG, "null tensor pointer");
@@ -116,10 +122,31 @@ SLAK_API int slak_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
+// Tensor-core route of the single-convolution entry points: bf16 activations, fp32 taps, one kernel side equal to 5
+// (K x 5, 5 x K, 5 x 5: every depthwise shape of a Decom SLaK Block) on a plane size the banded-Toeplitz kernels take.
+// K x 5 runs as the transposed family alone, 5 x K / 5 x 5 as the natural family alone (csrc/dwconv_tc_dgrad.cu).
+static bool single_uses_tc(int N, int C, int H, int W, int kh, int kw, int dtype, int wdtype) {
+  if (dtype != SLAK_BF16 || wdtype != SLAK_F32) return false;
+  if (kh != 5 && kw != 5) return false;
+  const int KL = kh == 5 ? kw : kh;
+  return tc::lk3_bwd_tc_supported(N, C, H, W, KL < 5 ? 5 : KL) && KL >= 5;
+}
+static int single_conv_tc(const void* in, const void* w, void* out, int N, int C, int H, int W, int kh, int kw, int flip,
+                          cudaStream_t st) {
+  if (kw == 5 && kh != 5)     // K x 5: long axis vertical -> transposed family
+    return tc::lk_conv_tc(in, (const float*)w, nullptr, nullptr, nullptr, out, nullptr, nullptr, N, C, H, W, kh, 5, flip, st);
+  return tc::lk_conv_tc(nullptr, nullptr, in, (const float*)w, nullptr, out, nullptr, nullptr, N, C, H, W, 5, kw, flip, st);
+}
+
+SLAK_API int slak_dwconv2d_uses_tc(int N, int C, int H, int W, int kh, int kw, int dtype, int wdtype) {
+  return (N > 0 && C > 0 && single_uses_tc(N, C, H, W, kh, kw, dtype, wdtype)) ? 1 : 0;
+}
+
 SLAK_API int slak_dwconv2d_fwd(const void* x, const void* w, void* y, int N, int C, int H, int W,
                                int kh, int kw, int dtype, int wdtype, void* stream) {
   int rc = check_conv_args(x, w, y, N, C, H, W, kh, kw, dtype, wdtype);
   if (rc) return rc;
+  if (single_uses_tc(N, C, H, W, kh, kw, dtype, wdtype)) return single_conv_tc(x, w, y, N, C, H, W, kh, kw, 0, (cudaStream_t)stream);
   return dwconv_simt_fwd(x, w, y, N, C, H, W, kh, kw, dtype, wdtype, /*flip=*/0, (cudaStream_t)stream);
 }
 
@@ -127,13 +154,21 @@ SLAK_API int slak_dwconv2d_bwd_data(const void* dy, const void* w, void* dx, int
                                     int W, int kh, int kw, int dtype, int wdtype, void* stream) {
   int rc = check_conv_args(dy, w, dx, N, C, H, W, kh, kw, dtype, wdtype);
   if (rc) return rc;
+  if (single_uses_tc(N, C, H, W, kh, kw, dtype, wdtype)) return single_conv_tc(dy, w, dx, N, C, H, W, kh, kw, 1, (cudaStream_t)stream);
   return dwconv_simt_fwd(dy, w, dx, N, C, H, W, kh, kw, dtype, wdtype, /*flip=*/1, (cudaStream_t)stream);
 }
 
+// the tensor-core weight gradient is the fused three-branch kernel with the one gradient tensor given for all three
+// branches: the wanted branch lands in dw, the other two go to scratch behind the kernel's own workspace
+static size_t single_wgrad_tc_scratch(int C, int KL) { return (((size_t)C * KL * 5 * sizeof(float)) + 255) / 256 * 256; }
+
 SLAK_API size_t slak_dwconv2d_bwd_filter_workspace(int N, int C, int H, int W, int kh, int kw,
                                                    int dtype) {
-  (void)dtype;
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0) return 0;
+  if (single_uses_tc(N, C, H, W, kh, kw, dtype, SLAK_F32)) {
+    const int KL = kh == 5 ? kw : kh;
+    return (tc::lk3_wgrad_tc_workspace(N, C, H, W, KL) + 255) / 256 * 256 + 3 * single_wgrad_tc_scratch(C, KL);
+  }
   return dwconv_simt_wgrad_workspace(N, C, H, W, kh, kw);
 }
 
@@ -142,9 +177,20 @@ SLAK_API int slak_dwconv2d_bwd_filter(const void* dy, const void* x, float* dw, 
                                       size_t workspace_bytes, void* stream) {
   int rc = check_conv_args(dy, x, dw, N, C, H, W, kh, kw, dtype, dtype);
   if (rc) return rc;
-  size_t need = dwconv_simt_wgrad_workspace(N, C, H, W, kh, kw);
+  const size_t need = slak_dwconv2d_bwd_filter_workspace(N, C, H, W, kh, kw, dtype);
   SLAK_REQUIRE(workspace && workspace_bytes >= need, SLAK_ERR_WORKSPACE,
                "bwd_filter workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if (single_uses_tc(N, C, H, W, kh, kw, dtype, SLAK_F32)) {
+    const int KL = kh == 5 ? kw : kh;
+    const size_t w0 = (tc::lk3_wgrad_tc_workspace(N, C, H, W, KL) + 255) / 256 * 256, sc = single_wgrad_tc_scratch(C, KL);
+    uint8_t* wsb = (uint8_t*)workspace;
+    float* t1 = (float*)(wsb + w0); float* t2 = (float*)(wsb + w0 + sc); float* t3 = (float*)(wsb + w0 + 2 * sc);
+    float* o1 = t1; float* o2 = t2; float* o3 = t3;
+    if (kw == 5 && kh != 5) o1 = dw;            // K x 5
+    else if (kh == 5 && kw != 5) o2 = dw;       // 5 x K
+    else o3 = dw;                               // 5 x 5
+    return tc::lk3_wgrad_tc(x, dy, dy, dy, o1, o2, o3, N, C, H, W, KL, workspace, (cudaStream_t)stream);
+  }
   return dwconv_simt_wgrad(dy, x, dw, N, C, H, W, kh, kw, dtype, workspace, (cudaStream_t)stream);
 }
 
@@ -317,6 +363,20 @@ SLAK_API int slak_mask_apply(float* const* w_ptrs, const float* const* mask_ptrs
   SLAK_REQUIRE(w_ptrs && mask_ptrs && numels, SLAK_ERR_BAD_ARG, "null pointer table");
   SLAK_REQUIRE(count <= 65535, SLAK_ERR_UNSUPPORTED, "too many tensors in one launch: %d", count);
   return mask_apply(w_ptrs, mask_ptrs, extra_ptrs, numels, count, max_numel, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_adamw_mask_ema_step(float* const* p, const float* const* g, float* const* m, float* const* v,
+                                      const float* const* mask, float* const* ema, const int64_t* numel, const double* lr,
+                                      const double* wd, const int32_t* chunk_tensor, const int64_t* chunk_off, int nchunks,
+                                      int chunk_elems, double beta1, double beta2, double eps, double ema_decay,
+                                      int64_t* step_dev, int do_adam, void* stream) {
+  SLAK_REQUIRE(nchunks >= 0 && chunk_elems > 0, SLAK_ERR_BAD_ARG, "bad chunk list");
+  if (nchunks == 0) return SLAK_OK;
+  SLAK_REQUIRE(p && numel && chunk_tensor && chunk_off && step_dev, SLAK_ERR_BAD_ARG, "null table");
+  SLAK_REQUIRE(!do_adam || (g && m && v && lr && wd), SLAK_ERR_BAD_ARG, "AdamW needs gradient / moment / lr / wd tables");
+  SLAK_REQUIRE(do_adam || mask || ema, SLAK_ERR_BAD_ARG, "nothing to do");
+  return adamw_mask_ema(p, g, m, v, mask, ema, numel, lr, wd, chunk_tensor, chunk_off, nchunks, chunk_elems, beta1, beta2,
+                        eps, ema_decay, step_dev, do_adam, (cudaStream_t)stream);
 }
 
 SLAK_API size_t slak_mask_prune_workspace(int64_t numel) { return mask_prune_workspace(numel); }

@@ -64,12 +64,12 @@ struct DgradParams {
   const float* addend_f32;         // [N,C,H,W] fp32 or nullptr (e.g. the shortcut gradient of a Block)
   __nv_bfloat16* out;              // bf16 result, or nullptr when out_f32 is given
   float* out_f32;
-  int N, C, H, W, KL, KN, flip, has_t, splits, units_per_c, per_cta;
+  int N, C, H, W, KL, KN, flip, has_t, has_n, splits, units_per_c, per_cta;
 };
 
 template <int T>
 __device__ __forceinline__ void build_toeplitz_pair(uint8_t* tp, const float* wts, const float* wns, int KL, int KN,
-                                                    bool has_t, int t0, int nthr) {
+                                                    bool has_t, bool has_n, int t0, int nthr) {
   constexpr int CH = T / 8;
   const int padn = KN / 2, padt = KL / 2;
   for (int ch = t0; ch < 5 * T * CH; ch += nthr) {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void build_toeplitz_pair(uint8_t* tp, const float* wt
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int tn = (k8 * 8 + j) - row + padn;
-      vn[j] = (tn >= 0 && tn < KN) ? wns[s * KN + tn] : 0.f;
+      vn[j] = (has_n && tn >= 0 && tn < KN) ? wns[s * KN + tn] : 0.f;
       const int tt = (k8 * 8 + j) - row + padt;
       vt[j] = (has_t && tt >= 0 && tt < KL) ? wts[tt * 5 + s] : 0.f;
     }
@@ -98,11 +98,12 @@ __device__ __forceinline__ void stage_taps(const DgradParams& P, int c, float* w
       const int src = P.flip ? ((KL - 1 - t) * 5 + (4 - s)) : i;
       wts[i] = P.wt[(size_t)c * KL * 5 + src];
     }
-  for (int i = t0; i < 5 * KN; i += nthr) {
-    const int r = i / KN, t = i - r * KN;
-    const int src = P.flip ? ((4 - r) * KN + (KN - 1 - t)) : i;
-    wns[i] = P.wn[(size_t)c * 5 * KN + src];
-  }
+  if (P.has_n)
+    for (int i = t0; i < 5 * KN; i += nthr) {
+      const int r = i / KN, t = i - r * KN;
+      const int src = P.flip ? ((4 - r) * KN + (KN - 1 - t)) : i;
+      wns[i] = P.wn[(size_t)c * 5 * KN + src];
+    }
 }
 
 template <int T, int CB, bool TMA>
@@ -135,7 +136,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   const int c_first = n_units > 0 ? (int)(g0 / upc) : 0;
   const int c_last = n_units > 0 ? (int)((g1 - 1) / upc) : -1;
   const int KL = P.KL, KN = P.KN, H = P.H, W = P.W;
-  const bool has_t = P.has_t != 0;
+  const bool has_t = P.has_t != 0, has_n = P.has_n != 0;
 
   constexpr int B_N_FULL = 0, B_N_EMPTY = kNStages, B_S_FULL = 2 * kNStages, B_S_EMPTY = B_S_FULL + kSStages,
                 B_T_FULL = B_S_EMPTY + kSStages, B_T_EMPTY = B_T_FULL + 1, B_ACC_FULL = B_T_EMPTY + 1,
@@ -163,7 +164,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     float* wns = wts + KL * 5;
     stage_taps(P, c_first, wts, wns, tid, kThreads);
     __syncthreads();
-    build_toeplitz_pair<T>(sm + Cf::kOffToep, wts, wns, KL, KN, has_t, tid, kThreads);
+    build_toeplitz_pair<T>(sm + Cf::kOffToep, wts, wns, KL, KN, has_t, has_n, tid, kThreads);
   }
   fence_proxy_async();
   if (warp == 2) tmem_alloc<Cf::kTmemCols>(smem_u32(tmem_slot));
@@ -180,7 +181,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           const long long g = g0 + i;
           const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
           const int n0 = PLANES * u;
-          {
+          if (has_n) {
             const int st = i % kNStages, ph = (i / kNStages) & 1;
             mbar_wait(BAR(B_N_EMPTY + st), ph ^ 1);
             const uint32_t dst = base + Cf::kOffXN + st * kSlot + kPad;
@@ -209,12 +210,16 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       PieceMap<CB> pm;
       pm.init(H, W, lane);
       const size_t plane_bytes = (size_t)H * W * 2;
-      for (int i = lj; i < n_units; i += kNStages) {
+      // Without the natural path (K x 5 alone) nothing but the two source slots paces the loaders, and a loader that
+      // shares a slot with another one could run two mbarrier phases ahead (a parity wait cannot tell phase k from
+      // k + 2): then only kSStages loaders work, each owning one source slot.
+      const int stride = has_n ? kNStages : kSStages;
+      for (int i = (has_n || lj < kSStages) ? lj : n_units; i < n_units; i += stride) {
         const long long g = g0 + i;
         const int c = (int)(g / upc), u = (int)(g - (long long)c * upc);
         const int n0 = PLANES * u;
         const int st = lj, ph = (i / kNStages) & 1;
-        mbar_wait(BAR(B_N_EMPTY + st), ph ^ 1);
+        if (has_n) mbar_wait(BAR(B_N_EMPTY + st), ph ^ 1);
         const int ss = i % kSStages, sph = (i / kSStages) & 1;
         if (has_t) mbar_wait(BAR(B_S_EMPTY + ss), sph ^ 1);
         const uint32_t tn = base + Cf::kOffXN + st * kSlot + kPad;
@@ -236,7 +241,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               }
             }
             if constexpr (CB == 2) {
-              load_plane_blocks_cb2<8>(pm, sn, tn, r0s, c0s, cnt, lane);
+              if (has_n) load_plane_blocks_cb2<8>(pm, sn, tn, r0s, c0s, cnt, lane);
               if (has_t) load_plane_blocks_cb2<8>(pm, stt, ts, r0s, c0s, cnt, lane);
             }
           }
@@ -244,7 +249,8 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           for (int q = qlo; q < qhi; ++q)
             if (n0 + q < P.N) {
               const size_t off = ((size_t)(n0 + q) * P.C + c) * plane_bytes;
-              load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.in_n) + off, tn, (q % PPU) * T, (q / PPU) * (T / 8), lane);
+              if (has_n)
+                load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.in_n) + off, tn, (q % PPU) * T, (q / PPU) * (T / 8), lane);
               if (has_t)
                 load_plane_block<CB>(pm, reinterpret_cast<const uint8_t*>(P.in_t) + off, ts, (q % PPU) * T, (q / PPU) * (T / 8), lane);
             }
@@ -254,7 +260,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(BAR(B_N_FULL + st));
+          if (has_n) mbar_arrive(BAR(B_N_FULL + st));
           if (has_t) mbar_arrive(BAR(B_S_FULL + ss));
         }
       }
@@ -275,19 +281,21 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int st = i % kNStages, ph = (i / kNStages) & 1;
         const int ab = i % kAccBufs, aph = (i / kAccBufs) & 1;
         mbar_wait(BAR(B_ACC_EMPTY + ab), aph ^ 1);
-        mbar_wait(BAR(B_N_FULL + st), ph);
-        tc_fence_after();
-        const uint32_t xn = base + Cf::kOffXN + st * kSlot + kPad;
         const uint32_t acc = tmem + ab * Cf::kAccCols;
+        if (has_n) {
+          mbar_wait(BAR(B_N_FULL + st), ph);
+          tc_fence_after();
+          const uint32_t xn = base + Cf::kOffXN + st * kSlot + kPad;
 #pragma unroll
-        for (int g = 0; g < UPS; ++g)
+          for (int g = 0; g < UPS; ++g)
 #pragma unroll
-          for (int r = 0; r < 5; ++r)
+            for (int r = 0; r < 5; ++r)
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk)
-              umma_bf16(acc + g * 2 * T, umma_desc_k_sw128(xn + (r - 2) * 128 + g * (T * 2) + kk * 32, 0),
-                        umma_desc_k_sw128(toep + r * (T * 128) + kk * 32, 0), idesc, (r | kk) != 0);
-        umma_commit(BAR(B_N_EMPTY + st));
+              for (int kk = 0; kk < KSTEPS; ++kk)
+                umma_bf16(acc + g * 2 * T, umma_desc_k_sw128(xn + (r - 2) * 128 + g * (T * 2) + kk * 32, 0),
+                          umma_desc_k_sw128(toep + r * (T * 128) + kk * 32, 0), idesc, (r | kk) != 0);
+          umma_commit(BAR(B_N_EMPTY + st));
+        }
         if (has_t) {
           mbar_wait(BAR(B_T_FULL), i & 1);
           tc_fence_after();
@@ -409,8 +417,13 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int n = PLANES * u + g * PPU + pl;
         const bool ok = (n < P.N) && (row < H);
         const size_t rbase = ((size_t)(n < P.N ? n : 0) * P.C + c) * plane_elems + (size_t)(row < H ? row : 0) * W;
-        tmem_ld_cols<T>(tmem + ((uint32_t)(e * 32) << 16) + ab * Cf::kAccCols + g * 2 * T, v);
-        tmem_ld_wait();
+        if (has_n) {
+          tmem_ld_cols<T>(tmem + ((uint32_t)(e * 32) << 16) + ab * Cf::kAccCols + g * 2 * T, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < T; ++k) v[k] = 0u;
+        }
         if (g == UPS - 1) {
           tc_fence_before();
           __syncwarp();
@@ -457,7 +470,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       mbar_wait(BAR(B_TP_EMPTY + set), ((k / NT) & 1) ^ 1);
       stage_taps(P, c, wts, wns, lane, 32);
       __syncwarp();
-      build_toeplitz_pair<T>(sm + Cf::kOffToep + set * Cf::kToepSet, wts, wns, KL, KN, has_t, lane, 32);
+      build_toeplitz_pair<T>(sm + Cf::kOffToep + set * Cf::kToepSet, wts, wns, KL, KN, has_t, has_n, lane, 32);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_TP_FULL + set));
@@ -483,7 +496,7 @@ static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParam
   return SLAK_OK;
 }
 
-// out = conv(in_t, wt [C,KL,5]) + conv(in_n, wn [C,5,KN]) + addend ; in_t/wt may be null together
+// out = conv(in_t, wt [C,KL,5]) + conv(in_n, wn [C,5,KN]) + addend ; in_t/wt may be null together, and so may in_n/wn
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
                const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
                cudaStream_t st) {
@@ -492,16 +505,17 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
   SLAK_REQUIRE((KL * 5 + 5 * KN) * 4 <= 4096, SLAK_ERR_UNSUPPORTED, "kernel side %d too large", KL);
   CUtensorMap mt, mn;
   memset(&mt, 0, sizeof(mt)); memset(&mn, 0, sizeof(mn));
+  SLAK_REQUIRE(in_t || in_n, SLAK_ERR_BAD_ARG, "lk_conv_tc needs at least one input");
   if (s.tma) {
     int rc;
-    if ((rc = make_plane_map(&mn, in_n, N, C, H, W))) return rc;
+    if ((rc = make_plane_map(&mn, in_n ? in_n : in_t, N, C, H, W))) return rc;
     if ((rc = make_plane_map(&mt, in_t ? in_t : in_n, N, C, H, W))) return rc;
   }
   DgradParams P;
   P.in_t = (const __nv_bfloat16*)in_t; P.in_n = (const __nv_bfloat16*)in_n;
   P.wt = wt; P.wn = wn; P.addend = (const __nv_bfloat16*)addend; P.out = (__nv_bfloat16*)out;
   P.addend_f32 = addend_f32; P.out_f32 = out_f32;
-  P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL; P.KN = KN; P.flip = flip; P.has_t = in_t ? 1 : 0;
+  P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL; P.KN = KN; P.flip = flip; P.has_t = in_t ? 1 : 0; P.has_n = in_n ? 1 : 0;
   if (s.tile == 64) return launch_dgrad<64, 16, true>(mt, mn, P, st);
   if (s.tile == 32) {
     if (s.cb == 8) return launch_dgrad<32, 8, false>(mt, mn, P, st);

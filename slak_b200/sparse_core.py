@@ -210,7 +210,8 @@ class Masking(object):
     # ------------------------------------------------------------------ per step
     def step(self):
         self.optimizer.step()
-        self.apply_mask()
+        if not getattr(self.optimizer, "fused_mask", False):     # slak_b200.optim.FusedAdamW applies the masks in its step
+            self.apply_mask()
         self.advance()
 
     def advance(self):

@@ -159,3 +159,31 @@ def test_error_behaviour():
         ops.dwconv2d_forward(x.permute(0, 1, 3, 2), m.weight.detach())
     with pytest.raises(ValueError):
         DepthWiseConv2dImplicitGEMM(4, 4)
+
+
+def test_single_conv_entry_points_route_bf16_slak_shapes_to_tensor_cores():
+    """The six frontend symbols (frontend.h:3-10) reach the tcgen05 kernels for bf16 K x 5 / 5 x K / 5 x 5 on every
+    SLaK-T stage geometry; fp32 (exact path), fp16, square kernels and planes above 62 x 62 stay on the CUDA cores."""
+    from slak_b200 import _lib
+    lib = _lib.load()
+    BF, F32, F16 = _lib.SLAK_BF16, _lib.SLAK_F32, _lib.SLAK_F16
+    for C, hw, K in ((96, 56, 51), (192, 28, 49), (384, 14, 47), (768, 7, 13)):
+        for kh, kw in ((K, 5), (5, K), (5, 5)):
+            assert lib.slak_dwconv2d_uses_tc(128, C, hw, hw, kh, kw, BF, F32) == 1
+            assert lib.slak_dwconv2d_uses_tc(128, C, hw, hw, kh, kw, F32, F32) == 0
+            assert lib.slak_dwconv2d_uses_tc(128, C, hw, hw, kh, kw, F16, F32) == 0
+    assert lib.slak_dwconv2d_uses_tc(32, 128, 96, 96, 51, 5, BF, F32) == 0
+    assert lib.slak_dwconv2d_uses_tc(32, 128, 32, 32, 31, 31, BF, F32) == 0
+    # the module surface under bf16: forward + backward through the tensor-core route against the oracle
+    torch.manual_seed(0)
+    m = DepthWiseConv2dImplicitGEMM(96, (51, 5)).to(DEV)
+    x = torch.randn(8, 96, 56, 56, device=DEV).bfloat16().requires_grad_(True)
+    y = m(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wq = orc.round_like(m.weight.detach().cpu(), torch.bfloat16).double()
+    y64 = orc.fwd_torch(x.detach().cpu().double(), wq)
+    dx64, dw64 = orc.grads_torch(x.detach().cpu().double(), wq, dy.cpu().double())
+    assert _rel_linf(y.detach().cpu(), y64) <= 2.0 ** -8 + 1e-5
+    assert _rel_linf(x.grad.cpu(), dx64) <= 2.0 ** -8 + 1e-5
+    assert m.weight.grad.dtype == torch.float32 and _rel_linf(m.weight.grad.cpu(), dw64) <= 1e-4
