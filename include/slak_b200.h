@@ -124,6 +124,13 @@ SLAK_API int slak_lk_branches_bwd_data(const void* dy1, const void* dy2, const v
 SLAK_API int slak_lk_branches_bwd_data_f32(const void* dy1, const void* dy2, const void* dy3, const float* w1,
                                            const float* w2, const float* w3, const float* addend, float* dx,
                                            void* tmp, int N, int C, int H, int W, int KL, int KS, void* stream);
+/* Inference form of the Decom layer after re-parameterisation (slak_b200.slak.ReparamLargeKernelConv.merge_kernel: the
+ * three BatchNorms folded as fuse_bn does, models/SLaK.py:49-58, the 5 x 5 kernel added into the centre of the 5 x KL
+ * one; the reference's merge_kernel :111-122 covers only the non-Decom layout):
+ *   y = dwconv_{KL x 5}(x, wv) + dwconv_{5 x KL}(x, wh) + bias[c]      x read once, y written once
+ * wv [C,1,KL,5], wh [C,1,5,KL], bias [C] fp32 (may be NULL); tensor-core shapes only (slak_lk_branches_uses_tc). */
+SLAK_API int slak_lk_merged_fwd(const void* x, const float* wv, const float* wh, const float* bias, void* y, int N, int C,
+                                int H, int W, int KL, int dtype, void* stream);
 SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS);
 SLAK_API int slak_lk_branches_bwd_filter(const void* x, const void* dy1, const void* dy2, const void* dy3,
                                          float* dw1, float* dw2, float* dw3, int N, int C, int H, int W,
@@ -276,6 +283,21 @@ SLAK_API size_t slak_mask_prune_workspace(int64_t numel);
 SLAK_API int slak_mask_prune_magnitude(const float* w, float* mask, int64_t numel,
                                        int64_t k, void* workspace,
                                        size_t workspace_bytes, void* stream);
+
+/* Growth by score (gradient_growth / momentum_growth, funcs.py:196-299): mask[i] = 1 at the k positions of largest
+ * |score[i]| among the positions whose mask is 0 (the reference sorts |score * (mask == 0)| descending and takes idx[:k];
+ * ties go to the lower flat index here).  Same workspace as slak_mask_prune_magnitude. */
+SLAK_API int slak_mask_grow_topk(const float* score, float* mask, int64_t numel, int64_t k, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+/* out[0] (device) = |x| of the k-th largest magnitude: SNIP's global threshold torch.topk(all_scores, keep)[-1]
+ * (sparse_core.py:36-38) without sorting 30 M scores. */
+SLAK_API int slak_select_kth_largest_abs(const float* x, int64_t numel, int64_t k, void* workspace, size_t workspace_bytes,
+                                         float* out, void* stream);
+/* 0/1 fp32 mask <-> bit mask, element i = bit (i % 32) of word i / 32; words holds (numel + 31) / 32 uint32.  For
+ * packed-mask checkpoints (the reference saves no masks and rebuilds them as weight != 0, sparse_core.py:158-172) and
+ * the 32x smaller mask broadcast. */
+SLAK_API int slak_mask_pack_bits(const float* mask, uint32_t* words, int64_t numel, void* stream);
+SLAK_API int slak_mask_unpack_bits(const uint32_t* words, float* mask, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }

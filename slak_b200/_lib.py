@@ -38,6 +38,7 @@ SIGNATURES = {
     "slak_lk_branches_bwd_uses_tc": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "slak_lk_branches_bwd_data": (_i, [_vp] * 8 + [_i] * 7 + [_vp]),
     "slak_lk_branches_bwd_data_f32": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
+    "slak_lk_merged_fwd": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "slak_lk_branches_bwd_filter_workspace": (_sz, [_i] * 6),
     "slak_lk_branches_bwd_filter": (_i, [_vp] * 7 + [_i] * 7 + [_vp, _sz, _vp]),
     "slak_block_conv_fwd_workspace": (_sz, [_i] * 4),
@@ -69,6 +70,10 @@ SIGNATURES = {
     "slak_adamw_mask_ema_step": (_i, [_vp] * 11 + [_i, _i] + [ctypes.c_double] * 4 + [_vp, _i, _vp]),
     "slak_mask_prune_workspace": (_sz, [_i64]),
     "slak_mask_prune_magnitude": (_i, [_vp, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "slak_mask_grow_topk": (_i, [_vp, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "slak_select_kth_largest_abs": (_i, [_vp, _i64, _i64, _vp, _sz, _vp, _vp]),
+    "slak_mask_pack_bits": (_i, [_vp, _vp, _i64, _vp]),
+    "slak_mask_unpack_bits": (_i, [_vp, _vp, _i64, _vp]),
 }
 
 

@@ -132,6 +132,16 @@ class FusedBlockFunction(torch.autograd.Function):
                 if nbt is not None:
                     nbt.add_(1)
             ops._count(3)
+        elif cfg.get("merged"):
+            # re-parameterised layer: one kernel, x read once and the sum written once; w3 carries the merged bias.  The
+            # LayerNorm kernel takes it as "three branches": u, u, u with scale (1, 0, 0) and no shift
+            y1 = y2 = y3 = ops.lk_merged_forward(xb, w1, w2, w3)
+            scale.zero_()
+            scale[0].fill_(1.0)
+            shift.zero_()
+            mean = istd = None
+            count = float(N * HW)
+            count_dev = None
         else:
             ys = ops.lk_branches_forward(xb, w1, w2, w3)
             y1, y2, y3 = ys
@@ -298,6 +308,11 @@ def fused_block_supported(block, x) -> bool:
         return False
     if not (torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16):
         return False
+    if hasattr(lk, "lkb_reparam_v"):           # re-parameterised Decom layer: inference only
+        N, C, H, W = x.shape
+        return (not torch.is_grad_enabled() and block.gamma is not None and lk.small_kernel_or_5() == 5 and C <= 1024 and
+                block.norm.data_format == "channels_last" and
+                ops.lk_branches_bwd_uses_tc(_Shape(N, C, H, W), lk.kernel_size, 5))
     if not (getattr(lk, "Decom", False) and hasattr(lk, "small_conv") and hasattr(lk, "LoRA1") and block.gamma is not None):
         return False
     if lk.small_kernel != 5 or not all(hasattr(b, "bn") for b in (lk.LoRA1, lk.LoRA2, lk.small_conv)):
@@ -332,6 +347,15 @@ class _Shape:
 
 def fused_block_forward(block, x):
     lk = block.large_kernel
+    if hasattr(lk, "lkb_reparam_v"):
+        v, h = lk.lkb_reparam_v, lk.lkb_reparam_h
+        cfg = {"training": False, "merged": True, "sync_bn": False, "process_group": None, "bn_eps": 0.0, "bn_momentum": 0.0,
+               "ln_eps": float(block.norm.eps), "running_mean": (None,) * 3, "running_var": (None,) * 3,
+               "num_batches_tracked": (None,) * 3}
+        return FusedBlockFunction.apply(
+            x, v.weight.detach(), h.weight.detach(), v.bias.detach(), None, None, None, None, None, None,
+            block.norm.weight, block.norm.bias, block.pwconv1.weight, block.pwconv1.bias, block.pwconv2.weight,
+            block.pwconv2.bias, block.gamma, None, cfg)
     bns = (lk.LoRA1.bn, lk.LoRA2.bn, lk.small_conv.bn)
     sync = isinstance(bns[0], torch.nn.SyncBatchNorm)
     track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)

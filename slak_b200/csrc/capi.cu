@@ -29,7 +29,7 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
 int lk3_fwd_tc_splits(int N, int C, int H, int W);
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
                const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
-               cudaStream_t st);
+               cudaStream_t st, const float* bias = nullptr);
 int mlp_parts(int M, int N);
 int mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const void* aux_h, void* out0, void* out1,
                 float* colpart, int M, int N, int K, cudaStream_t st);
@@ -80,6 +80,10 @@ int mask_apply(float* const* w_ptrs, const float* const* m_ptrs, float* const* e
 size_t mask_prune_workspace(int64_t n);
 int mask_prune_magnitude(const float* w, float* mask, int64_t n, int64_t k, void* workspace,
                          cudaStream_t st);
+int mask_grow_topk(const float* score, float* mask, int64_t n, int64_t k, void* workspace, cudaStream_t st);
+int select_kth_largest_abs(const float* x, int64_t n, int64_t k, void* workspace, float* out, cudaStream_t st);
+int mask_pack_bits(const float* mask, uint32_t* words, int64_t n, cudaStream_t st);
+int mask_unpack_bits(const uint32_t* words, float* mask, int64_t n, cudaStream_t st);
 
 // optim.cu
 int adamw_mask_ema(float* const* p, const float* const* g, float* const* m, float* const* v, const float* const* mask,
@@ -247,6 +251,18 @@ SLAK_API int slak_lk_branches_bwd_data_f32(const void* dy1, const void* dy2, con
   return tc::lk_conv_tc(dy1, w1, dy2, w2, tmp, nullptr, addend, dx, N, C, H, W, KL, KL, /*flip=*/1, st);
 }
 
+// Inference form of the Decom large-kernel layer after re-parameterisation (three BatchNorms folded, 5 x 5 merged into
+// the 5 x K kernel): y = dwconv_{KL x 5}(x, wv) + dwconv_{5 x KL}(x, wh) + bias, x read once, y written once.
+SLAK_API int slak_lk_merged_fwd(const void* x, const float* wv, const float* wh, const float* bias, void* y, int N, int C,
+                                int H, int W, int KL, int dtype, void* stream) {
+  int rc = check_conv_args(x, wv, y, N, C, H, W, KL, 5, dtype, SLAK_F32);
+  if (rc) return rc;
+  SLAK_REQUIRE(wh, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, 5, dtype), SLAK_ERR_UNSUPPORTED,
+               "slak_lk_merged_fwd covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
+  return tc::lk_conv_tc(x, wv, x, wh, nullptr, y, nullptr, nullptr, N, C, H, W, KL, KL, /*flip=*/0, (cudaStream_t)stream, bias);
+}
+
 SLAK_API size_t slak_lk_branches_bwd_filter_workspace(int N, int C, int H, int W, int KL, int KS) {
   (void)KS;
   if (N <= 0 || C <= 0 || KL <= 0) return 0;
@@ -389,6 +405,32 @@ SLAK_API int slak_mask_prune_magnitude(const float* w, float* mask, int64_t nume
   SLAK_REQUIRE(workspace && workspace_bytes >= mask_prune_workspace(numel), SLAK_ERR_WORKSPACE,
                "prune workspace too small");
   return mask_prune_magnitude(w, mask, numel, k, workspace, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_mask_grow_topk(const float* score, float* mask, int64_t numel, int64_t k, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  SLAK_REQUIRE(score && mask, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(numel >= 0 && numel < (1ll << 32), SLAK_ERR_UNSUPPORTED, "numel %lld out of range", (long long)numel);
+  SLAK_REQUIRE(workspace && workspace_bytes >= mask_prune_workspace(numel), SLAK_ERR_WORKSPACE, "select workspace too small");
+  return mask_grow_topk(score, mask, numel, k, workspace, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_select_kth_largest_abs(const float* x, int64_t numel, int64_t k, void* workspace, size_t workspace_bytes,
+                                         float* out, void* stream) {
+  SLAK_REQUIRE(x && out, SLAK_ERR_BAD_ARG, "null tensor pointer");
+  SLAK_REQUIRE(numel > 0 && numel < (1ll << 32) && k >= 1 && k <= numel, SLAK_ERR_BAD_ARG, "need 1 <= k <= numel < 2^32");
+  SLAK_REQUIRE(workspace && workspace_bytes >= mask_prune_workspace(numel), SLAK_ERR_WORKSPACE, "select workspace too small");
+  return select_kth_largest_abs(x, numel, k, workspace, out, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_mask_pack_bits(const float* mask, uint32_t* words, int64_t numel, void* stream) {
+  SLAK_REQUIRE(mask && words && numel >= 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return mask_pack_bits(mask, words, numel, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_mask_unpack_bits(const uint32_t* words, float* mask, int64_t numel, void* stream) {
+  SLAK_REQUIRE(mask && words && numel >= 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return mask_unpack_bits(words, mask, numel, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -62,6 +62,7 @@ struct DgradParams {
   const float* wn;                 // [C][5][KN] taps of the natural path
   const __nv_bfloat16* addend;     // [N,C,H,W] or nullptr
   const float* addend_f32;         // [N,C,H,W] fp32 or nullptr (e.g. the shortcut gradient of a Block)
+  const float* bias;               // [C] fp32 or nullptr: per-channel constant added before rounding (merged BN shifts)
   __nv_bfloat16* out;              // bf16 result, or nullptr when out_f32 is given
   float* out_f32;
   int N, C, H, W, KL, KN, flip, has_t, has_n, splits, units_per_c, per_cta;
@@ -429,6 +430,11 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));
         }
+        if (P.bias) {
+          const float bv = __ldg(P.bias + c);
+#pragma unroll
+          for (int k = 0; k < T; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + bv);
+        }
         if (has_t) {
 #pragma unroll
           for (int ck = 0; ck < T / 4; ++ck) {
@@ -499,7 +505,7 @@ static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParam
 // out = conv(in_t, wt [C,KL,5]) + conv(in_n, wn [C,5,KN]) + addend ; in_t/wt may be null together, and so may in_n/wn
 int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float* wn, const void* addend, void* out,
                const float* addend_f32, float* out_f32, int N, int C, int H, int W, int KL, int KN, int flip,
-               cudaStream_t st) {
+               cudaStream_t st, const float* bias) {
   const TcShape s = tc_shape(H, W);
   SLAK_REQUIRE(s.tile != 0, SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   SLAK_REQUIRE((KL * 5 + 5 * KN) * 4 <= 4096, SLAK_ERR_UNSUPPORTED, "kernel side %d too large", KL);
@@ -514,7 +520,7 @@ int lk_conv_tc(const void* in_t, const float* wt, const void* in_n, const float*
   DgradParams P;
   P.in_t = (const __nv_bfloat16*)in_t; P.in_n = (const __nv_bfloat16*)in_n;
   P.wt = wt; P.wn = wn; P.addend = (const __nv_bfloat16*)addend; P.out = (__nv_bfloat16*)out;
-  P.addend_f32 = addend_f32; P.out_f32 = out_f32;
+  P.addend_f32 = addend_f32; P.out_f32 = out_f32; P.bias = bias;
   P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL; P.KN = KN; P.flip = flip; P.has_t = in_t ? 1 : 0; P.has_n = in_n ? 1 : 0;
   if (s.tile == 64) return launch_dgrad<64, 16, true>(mt, mn, P, st);
   if (s.tile == 32) {

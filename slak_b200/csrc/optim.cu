@@ -10,7 +10,7 @@
 // _single_tensor_adam with decoupled_weight_decay):
 //   p   = p * (1 - lr * wd)
 //   m   = lerp(m, g, 1 - beta1)                      weight < 0.5 form: m + w * (g - m)
-//   v   = v * beta2 + (1 - beta2) * g * g
+//   v   = v * beta2 + (1 - beta2) * (g * g)
 //   den = sqrt(v) * (1 / sqrt(1 - beta2^t)) + eps    (torch divides by a scalar through its reciprocal)
 //   p   = p + (-(lr / (1 - beta1^t))) * (m / den)
 //   p   = p * mask                                    IEEE multiply: a pruned negative weight becomes -0.0
@@ -62,7 +62,7 @@ adamw_mask_ema_kernel(AdamTables T, int chunk_elems, double beta1, double beta2,
       float mv = m[i], vv = v[i];
       pv = pv * decay_w;
       mv = __fmaf_rn(w1, gv - mv, mv);
-      vv = __fmaf_rn(w2 * gv, gv, vv * b2);
+      vv = __fmaf_rn(w2, __fmul_rn(gv, gv), __fmul_rn(vv, b2));      // addcmul: self + value * (t1 * t2)
       const float den = __fadd_rn(__fmul_rn(__fsqrt_rn(vv), inv_bc2s), epsf);
       pv = __fmaf_rn(neg_step, __fdiv_rn(mv, den), pv);
       m[i] = mv;

@@ -237,6 +237,26 @@ def lk_branches_forward(x, w1, w2, w3=None):
     return y1, y2, y3
 
 
+def lk_merged_forward(x, wv, wh, bias=None):
+    """Inference form of the re-parameterised Decom layer: y = dwconv_{KLx5}(x, wv) + dwconv_{5xKL}(x, wh) + bias, one
+    tcgen05 kernel (x read once, y written once).  bf16 tensor-core shapes only (lk_branches_bwd_uses_tc)."""
+    for t, nm in ((x, "input"), (wv, "wv"), (wh, "wh")):
+        _check_input(t, nm)
+    N, C, H, W = x.shape
+    KL = wv.size(2)
+    if tuple(wv.shape) != (C, 1, KL, 5) or tuple(wh.shape) != (C, 1, 5, KL) or wv.dtype != torch.float32 or wh.dtype != torch.float32:
+        raise RuntimeError("expected fp32 kernels [C,1,KL,5] and [C,1,5,KL]")
+    b = None if bias is None else bias.detach().float().contiguous()
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        rc = lib.slak_lk_merged_fwd(x.data_ptr(), wv.data_ptr(), wh.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(),
+                                    N, C, H, W, KL, _lib.dtype_code(x.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "slak_lk_merged_fwd")
+    _count(1)
+    return y
+
+
 def lk_branches_backward_data(dy1, dy2, dy3, w1, w2, w3):
     """dx = dgrad(dy1,w1) + dgrad(dy2,w2) + dgrad(dy3,w3); tensor-core shapes only."""
     for t, nm in ((dy1, "dy1"), (dy2, "dy2"), (dy3, "dy3"), (w1, "w1"), (w2, "w2"), (w3, "w3")):

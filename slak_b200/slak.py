@@ -130,7 +130,7 @@ class ReparamLargeKernelConv(nn.Module):
 
     def branches(self):
         """The conv_bn branches that are summed, in the reference's order."""
-        if hasattr(self, "lkb_reparam"):
+        if hasattr(self, "lkb_reparam") or hasattr(self, "lkb_reparam_v"):
             return []
         out = [self.LoRA1, self.LoRA2] if self.Decom else [self.lkb_origin]
         if hasattr(self, "small_conv"):
@@ -139,13 +139,22 @@ class ReparamLargeKernelConv(nn.Module):
 
     def _fused_ok(self, x):
         # the fused three-branch node needs the Decom layout with a small branch, no conv bias, fp32 taps
-        return (self.Decom and hasattr(self, "small_conv") and x.is_cuda and x.dim() == 4 and
+        return (self.Decom and hasattr(self, "small_conv") and hasattr(self, "LoRA1") and x.is_cuda and x.dim() == 4 and
                 x.dtype in (torch.float32, torch.float16, torch.bfloat16) and
                 self.LoRA1.conv.bias is None and self.LoRA1.conv.weight.dtype == torch.float32)
 
     def forward(self, inputs):
         if hasattr(self, "lkb_reparam"):
             return self.lkb_reparam(inputs)
+        if hasattr(self, "lkb_reparam_v"):
+            # re-parameterised Decom layout (merge_kernel below): K x 5 (+ bias) and 5 x K; one tcgen05 kernel when no
+            # gradient is needed and the shape allows, else the two operator modules
+            v, h = self.lkb_reparam_v, self.lkb_reparam_h
+            if (inputs.is_cuda and inputs.dtype == torch.bfloat16 and inputs.dim() == 4 and not
+                    (torch.is_grad_enabled() and (inputs.requires_grad or v.weight.requires_grad)) and
+                    ops.lk_branches_bwd_uses_tc(inputs, self.kernel_size, 5) and self.small_kernel_or_5() == 5):
+                return ops.lk_merged_forward(inputs.contiguous(), v.weight.detach(), h.weight.detach(), v.bias)
+            return v(inputs) + h(inputs)
         if self._fused_ok(inputs):
             # one node for the three convolutions (x read once; tensor cores where the shape allows),
             # then the reference's per-branch BN and sum (models/SLaK.py:93-95)
@@ -158,6 +167,28 @@ class ReparamLargeKernelConv(nn.Module):
             out = out + o
         return out
 
+    def small_kernel_or_5(self):
+        return 5 if self.small_kernel is None else self.small_kernel
+
+    def get_equivalent_decom(self):
+        """Inference re-parameterisation of the Decom layout (the reference's
+        merge_kernel, models/SLaK.py:102-122, only covers `lkb_origin`): each BatchNorm folded into its conv as fuse_bn
+        does (:49-58), the small x small kernel added into the centre of the small x K one.  Returns
+        (kernel K x small, kernel small x K, bias)."""
+        def fold(branch):
+            if hasattr(branch, "bn"):
+                return fuse_bn(branch.conv, branch.bn)
+            return branch.conv.weight, torch.zeros(branch.conv.weight.size(0), device=branch.conv.weight.device)
+        kv, bv = fold(self.LoRA1)
+        kh, bh = fold(self.LoRA2)
+        bias = bv + bh
+        if hasattr(self, "small_conv"):
+            ks, bs = fold(self.small_conv)
+            p = (self.kernel_size - self.small_kernel) // 2
+            kh = kh + F.pad(ks, [p, p, 0, 0])
+            bias = bias + bs
+        return kv, kh, bias
+
     def get_equivalent_kernel_bias(self):
         eq_k, eq_b = fuse_bn(self.lkb_origin.conv, self.lkb_origin.bn)
         if hasattr(self, "small_conv"):
@@ -168,6 +199,18 @@ class ReparamLargeKernelConv(nn.Module):
         return eq_k, eq_b
 
     def merge_kernel(self):
+        if self.Decom and hasattr(self, "LoRA1"):
+            kv, kh, bias = self.get_equivalent_decom()
+            c = self.LoRA1.conv
+            self.lkb_reparam_v = get_conv2d(c.in_channels, c.out_channels, tuple(kv.shape[2:]), 1, None, 1, c.groups, True)
+            self.lkb_reparam_h = get_conv2d(c.in_channels, c.out_channels, tuple(kh.shape[2:]), 1, None, 1, c.groups, False)
+            self.lkb_reparam_v.weight.data = kv.detach().clone()
+            self.lkb_reparam_v.bias.data = bias.detach().clone()
+            self.lkb_reparam_h.weight.data = kh.detach().clone()
+            for name in ("LoRA1", "LoRA2", "small_conv"):
+                if hasattr(self, name):
+                    self.__delattr__(name)
+            return
         eq_k, eq_b = self.get_equivalent_kernel_bias()
         conv = self.lkb_origin.conv
         self.lkb_reparam = get_conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride,

@@ -44,12 +44,24 @@ def SNIP(net, keep_ratio, train_dataloader, device, masks, args):
     scores = [torch.abs(w * w.grad) for name, w in net.named_parameters() if name in masks]
     flat = torch.cat([s.flatten() for s in scores])
     keep = int(len(flat) * keep_ratio)
-    threshold, _ = torch.topk(flat, keep, sorted=True)
-    cut = threshold[-1]
-    out = []
-    for s in scores:
-        m = (s > cut).float()
-        out.append(float((m == 0).sum().item() / m.numel()))
+    if flat.is_cuda and flat.dtype == torch.float32 and 1 <= keep <= flat.numel() < (1 << 32):
+        # torch.topk(flat, keep)[-1] = the keep-th largest score: device radix select instead of sorting ~30 M scores
+        lib = _lib.load()
+        ws = torch.empty(max(int(lib.slak_mask_prune_workspace(flat.numel())), 4096), dtype=torch.uint8, device=flat.device)
+        cut = torch.empty(1, dtype=torch.float32, device=flat.device)
+        with torch.cuda.device(flat.device):
+            rc = lib.slak_select_kth_largest_abs(flat.data_ptr(), flat.numel(), keep, ws.data_ptr(), ws.numel(), cut.data_ptr(),
+                                                 _lib.current_stream_ptr())
+        _lib.check(rc, "slak_select_kth_largest_abs")
+        zeros = torch.stack([(s <= cut).sum() for s in scores]).tolist()      # one device -> host transfer
+        out = [z / s.numel() for z, s in zip(zeros, scores)]
+    else:
+        threshold, _ = torch.topk(flat, keep, sorted=True)
+        cut = threshold[-1]
+        out = []
+        for s in scores:
+            m = (s > cut).float()
+            out.append(float((m == 0).sum().item() / m.numel()))
     net.zero_grad()
     return out
 
@@ -344,19 +356,88 @@ class Masking(object):
             print("{0}: {1}->{2}, density: {3:.3f}".format(name, self.name2nonzeros[name], c, c / float(m.numel())))
         print("Prune rate: {0}\n".format(self.prune_rate))
 
+    def fired_masks_update(self):
+        """sparse_core.py:388-402: positions that have ever been active (used by the `random_unfired` growth mode)."""
+        if not hasattr(self, "fired_masks"):
+            self.fired_masks = {}
+        layer_fired = {}
+        fired_total, total = 0.0, 0.0
+        for name, _ in self._masked_params():
+            prev = self.fired_masks.get(name)
+            cur = self.masks[name].data.byte()
+            self.fired_masks[name] = cur if prev is None else (cur | prev.data.byte())
+            f = float(self.fired_masks[name].sum().item())
+            fired_total += f
+            total += float(self.fired_masks[name].numel())
+            layer_fired[name] = f / float(self.fired_masks[name].numel())
+        total_fired = fired_total / max(total, 1.0)
+        print("The percentage of the total fired weights is:", total_fired)
+        return layer_fired, total_fired
+
+    # ------------------------------------------------------------------ packed masks (checkpoint / broadcast)
+    def _pack(self, m):
+        """fp32 0/1 mask -> int32 words, 32 elements per word (device kernel on CUDA, torch ops on CPU)."""
+        n = m.numel()
+        words = torch.empty((n + 31) // 32, dtype=torch.int32, device=m.device)
+        if m.is_cuda and m.dtype == torch.float32 and m.is_contiguous():
+            with torch.cuda.device(m.device):
+                rc = _lib.load().slak_mask_pack_bits(m.data_ptr(), words.data_ptr(), n, _lib.current_stream_ptr())
+            _lib.check(rc, "slak_mask_pack_bits")
+            return words
+        bits = torch.zeros(words.numel() * 32, dtype=torch.int64, device=m.device)
+        bits[:n] = (m.reshape(-1) != 0).long()
+        w = (bits.view(-1, 32) << torch.arange(32, device=m.device)).sum(1)
+        return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+
+    def _unpack_into(self, words, m):
+        n = m.numel()
+        words = words.to(device=m.device, dtype=torch.int32).contiguous()
+        if m.is_cuda and m.dtype == torch.float32 and m.is_contiguous():
+            with torch.cuda.device(m.device):
+                rc = _lib.load().slak_mask_unpack_bits(words.data_ptr(), m.data_ptr(), n, _lib.current_stream_ptr())
+            _lib.check(rc, "slak_mask_unpack_bits")
+            return
+        w = words.long() & 0xFFFFFFFF
+        bits = ((w.view(-1, 1) >> torch.arange(32, device=m.device)) & 1).reshape(-1)[:n]
+        m.copy_(bits.view_as(m).float())
+
+    def state_dict(self):
+        """Masks as bit masks (32x smaller than the fp32 masks) plus the schedule state.  The reference saves no masks:
+        `--sparse_init resume` rebuilds them as `weight != 0` (sparse_core.py:158-172), which loses every active weight
+        that happens to be exactly zero and the prune-rate schedule position."""
+        return {"steps": self.steps, "prune_rate": self.prune_rate,
+                "decay": self.prune_rate_decay.cosine_stepper.state_dict() if self.prune_rate_decay is not None else None,
+                "masks": {n: (self._pack(m).cpu(), tuple(m.shape)) for n, m in self.masks.items()}}
+
+    def load_state_dict(self, sd):
+        self.steps = int(sd["steps"])
+        self.prune_rate = sd["prune_rate"]
+        if sd.get("decay") is not None and self.prune_rate_decay is not None:
+            self.prune_rate_decay.cosine_stepper.load_state_dict(sd["decay"])
+        for n in list(self.masks):
+            if n not in sd["masks"]:
+                self.masks.pop(n)                      # a layer that went dense at init time
+        for n, (words, shape) in sd["masks"].items():
+            if n not in self.masks or tuple(self.masks[n].shape) != tuple(shape):
+                raise KeyError(f"mask {n} {tuple(shape)} does not match the attached model")
+            self._unpack_into(words, self.masks[n])
+        self._table = None
+        self.apply_mask()
+
     def _sync_masks(self):
-        """Every rank takes rank 0's masks (sparse_core.py:404-407), sent as one uint8 buffer."""
+        """Every rank takes rank 0's masks (sparse_core.py:404-407): one broadcast of the bit-packed masks (the
+        reference broadcasts every fp32 mask separately, on every step)."""
         if not getattr(self.args, "distributed", False):
             return
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or not self.masks:
             return
-        flat = torch.cat([m.reshape(-1).to(torch.uint8) for m in self.masks.values()])
+        packed = [self._pack(m) for m in self.masks.values()]
+        flat = torch.cat(packed)
         dist.broadcast(flat, src=0)
         off = 0
-        for m in self.masks.values():
-            n = m.numel()
-            m.copy_(flat[off:off + n].view_as(m).float())
-            off += n
+        for m, w in zip(self.masks.values(), packed):
+            self._unpack_into(flat[off:off + w.numel()], m)
+            off += w.numel()
 
     synchronism_masks = _sync_masks

@@ -57,3 +57,65 @@ def test_mask_apply_multi_tensor_ieee_semantics():
         assert np.array_equal((w * m).numpy().view(np.uint32), a.cpu().numpy().view(np.uint32))   # -0.0 preserved
         if b is not None:
             assert torch.equal(e * m, b.cpu())
+
+
+# ---- f4: SNIP init, gradient / momentum growth on the device kernels, packed masks -------------------------------
+@pytest.mark.parametrize("init,growth", [("snip", "random"), ("uniform", "gradient"), ("uniform", "momentum")])
+def test_snip_and_score_growth_modes_match_reference_golden_gpu(init, growth):
+    """The golden runs of the reference's sparse_core.Masking with sparse_init=snip and growth gradient / momentum,
+    replayed on CUDA: SNIP's threshold by device radix select, growth by slak_mask_grow_topk; masks bit-identical."""
+    replay(init, False, torch.device("cuda"), growth_mode=growth)
+
+
+@pytest.mark.parametrize("numel,k", [(1, 1), (300, 17), (4096, 0), (5000, 5000), (100003, 40001), (2_000_000, 700_001)])
+def test_grow_kernel_equals_stable_descending_sort(numel, k):
+    g = torch.Generator().manual_seed(3 * numel + k)
+    score = torch.randn(numel, generator=g)
+    score[torch.rand(numel, generator=g) < 0.2] = 0.0
+    if numel > 40:
+        score[7:numel // 3] = score[7 + numel // 3: 2 * (numel // 3)].abs()          # ties at non-zero magnitudes
+    mask = (torch.rand(numel, generator=g) < 0.5).float()
+    want = mask.clone()
+    s = (score * (mask == 0).float()).abs()
+    _, idx = torch.sort(s, descending=True, stable=True)
+    want[idx[:k]] = 1.0
+    lib = _lib.load()
+    sd, md = score.cuda(), mask.cuda()
+    ws = torch.empty(max(lib.slak_mask_prune_workspace(numel), 4096), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.slak_mask_grow_topk(sd.data_ptr(), md.data_ptr(), numel, k, ws.data_ptr(), ws.numel(),
+                                       torch.cuda.current_stream().cuda_stream), "grow")
+    assert torch.equal(md.cpu(), want)
+
+
+@pytest.mark.parametrize("numel,k", [(1, 1), (1000, 1), (1000, 1000), (100003, 60000), (3_000_000, 1_800_000)])
+def test_select_kth_largest_equals_topk(numel, k):
+    x = torch.randn(numel, generator=torch.Generator().manual_seed(numel + k)).abs()
+    x[::7] = 0.0
+    lib = _lib.load()
+    xd = x.cuda()
+    ws = torch.empty(max(lib.slak_mask_prune_workspace(numel), 4096), dtype=torch.uint8, device="cuda")
+    out = torch.empty(1, device="cuda")
+    _lib.check(lib.slak_select_kth_largest_abs(xd.data_ptr(), numel, k, ws.data_ptr(), ws.numel(), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "select")
+    assert out.item() == torch.topk(x, k, sorted=True)[0][-1].item()
+
+
+def test_packed_mask_checkpoint_round_trip_gpu_and_cpu_agree():
+    from slak_b200.sparse_core import Masking
+    mask = replay("uniform", False, torch.device("cuda"))
+    sd = mask.state_dict()
+    total_bits = sum(w.numel() * 32 for w, _ in sd["masks"].values())
+    assert total_bits < 33 * sum(m.numel() for m in mask.masks.values()) // 32 + 32 * len(mask.masks) * 32
+    for n, m in mask.masks.items():                                  # device pack == host pack, bit for bit
+        assert torch.equal(Masking._pack(mask, m).cpu(), Masking._pack(mask, m.cpu()))
+    before = {n: m.clone() for n, m in mask.masks.items()}
+    steps, rate = mask.steps, mask.prune_rate
+    for m in mask.masks.values():
+        m.fill_(1.0)
+    mask.steps, mask.prune_rate = 0, 0.0
+    mask.load_state_dict(sd)
+    assert mask.steps == steps and mask.prune_rate == rate
+    for n in before:
+        assert torch.equal(mask.masks[n], before[n])
+    for name, p in mask._masked_params():                            # load re-applies the masks
+        assert torch.all(p.data[before[name] == 0] == 0)
