@@ -59,6 +59,7 @@ def parse():
     p.add_argument("--cpu-batch", type=int, default=0, help="images per CPU-arm step (0 = sized so the run takes ~2 min)")
     p.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUTLASS ext (oracle/_ref/ext) on the GPU")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of slak_b200.optim.FusedAdamW")
     p.add_argument("--watchdog", type=float, default=1500.0, help="abort the process after this many seconds")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     a = p.parse_args()
@@ -330,7 +331,16 @@ def run_ours(args):
     # data parallelism = gradient all-reduce only (main.py:374-376): flat gradient buffer, buckets all-reduced on a side
     # stream as backward produces them (slak_b200/ddp.py); identical initial weights by broadcast
     dp = ddp.GradientAllReducer(net, bucket_mb=25.0) if world > 1 else None
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+    # gradients live in one flat buffer (static addresses for the graph and for the fused optimizer's pointer tables)
+    flat = dp if dp is not None else ddp.FlatGradients(net)
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+    else:
+        # this library's multi-tensor AdamW (+ mask apply when sparse): one launch, device-side step counter
+        from slak_b200.optim import FusedAdamW
+        decay = [p for p in params if p.dim() > 1]
+        no_decay = [p for p in params if p.dim() <= 1]       # optim_factory.py:73-112: no weight decay on 1-d tensors
+        opt = FusedAdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-3)
 
     B = args.batch
     IMG = cfg["img"]
@@ -353,13 +363,12 @@ def run_ours(args):
         margs.distributed = False                  # SNIP's `sampler.set_epoch` is for a real DistributedSampler
         mask.add_module(net)
         margs.distributed = world > 1
+        if not args.torch_adamw:
+            opt.attach_masking(mask)                   # p *= mask inside the optimizer launch
 
     def step_eager():
         # optimizer.zero_grad() as in engine.py:74-86: under graph capture the gradients live in the graph's private pool
-        if dp is None:
-            opt.zero_grad(set_to_none=True)
-        else:
-            dp.zero_grad()
+        flat.zero_grad()
         for k in range(UF):                              # engine.py:52-80: loss /= update_freq, backward every micro-step
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 out = net(x_dev[k * B:(k + 1) * B])
@@ -372,7 +381,7 @@ def run_ours(args):
         if dp is not None:
             dp.finish()
         opt.step()
-        if mask is not None:
+        if mask is not None and not getattr(opt, "fused_mask", False):
             mask.apply_mask()                            # Masking.step() = optimizer.step(); apply_mask(); advance()
         return loss
 

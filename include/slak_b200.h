@@ -167,6 +167,22 @@ SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const doubl
                                    const float* const* bnb, float* const* rmean, float* const* rvar, float eps,
                                    float momentum, int C, float* scale, float* shift, float* mean, float* istd,
                                    void* stream);
+/* SyncBatchNorm (models/SLaK.py:24-28) with the statistics exchange FUSED into the finalize kernels: a one-shot
+ * all-reduce over NVLink peer memory instead of one NCCL collective per BatchNorm (torch's SyncBatchNorm issues 3
+ * all_gathers per Block forward and 3 all_reduces per backward, torch/nn/modules/_functions.py:49,74,158).
+ * peer_bases: HOST array of `world` device pointers, entry r = rank r's symmetric buffer mapped into this process
+ * (torch.distributed._symmetric_memory supplies allocation and mapping); every rank's payload for this call site sits at
+ * slot_off (fwd: double sums[C][6], count, [global count out]; bwd: float S[4][C]), flag_off addresses `world` uint32
+ * flags of the site, epoch_dev is the site's device-side call counter (bumped by the call).  Ranks signal, wait for
+ * all peers and add the payloads in rank order (bitwise identical results on every rank).  world <= 8. */
+SLAK_API int slak_bn3_finalize_fwd_sync(const void* const* peer_bases, size_t slot_off, size_t flag_off, int rank, int world,
+                                        uint32_t* epoch_dev, const float* const* bnw, const float* const* bnb,
+                                        float* const* rmean, float* const* rvar, float eps, float momentum, int C,
+                                        float* scale, float* shift, float* mean, float* istd, void* stream);
+SLAK_API int slak_bn3_finalize_bwd_sync(const void* const* peer_bases, size_t slot_off, size_t flag_off, int rank, int world,
+                                        uint32_t* epoch_dev, const double* count_dev, const float* const* bnw,
+                                        const float* mean, const float* istd, int C, float* coef, float* dbnw, float* dbnb,
+                                        void* stream);
 SLAK_API int slak_bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean,
                                   const float* const* rvar, float eps, int C, float* scale, float* shift,
                                   void* stream);

@@ -44,6 +44,8 @@ SIGNATURES = {
     "slak_block_conv_fwd_workspace": (_sz, [_i] * 4),
     "slak_block_conv_fwd": (_i, [_vp] * 9 + [_sz] + [_i] * 5 + [_vp]),
     "slak_bn3_finalize_fwd": (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
+    "slak_bn3_finalize_fwd_sync": (_i, [_vp, _sz, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
+    "slak_bn3_finalize_bwd_sync": (_i, [_vp, _sz, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "slak_bn3_eval_affine": (_i, [_vp] * 4 + [ctypes.c_float, _i, _vp, _vp, _vp]),
     "slak_bn3_sum_ln_fwd": (_i, [_vp] * 7 + [ctypes.c_float] + [_vp] * 3 + [_i] * 3 + [_vp]),
     "slak_block_residual_fwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),

@@ -22,7 +22,7 @@ import os
 import torch
 import torch.nn.functional as F
 
-from . import _lib, ops
+from . import _lib, ops, syncbn
 
 
 def _p(t):
@@ -66,10 +66,11 @@ def _wgrad(lib, st, p, q, M, Ma, Nb):
     return _colsum(lib, part, st).view(Ma, Nb)
 
 
-def _colsum(lib, part2d, st):
+def _colsum(lib, part2d, st, out=None):
     """Fixed-order sum over the per-CTA partial rows [rows, cols] -> [cols] (one small launch of this library)."""
     rows, cols = part2d.shape
-    out = torch.empty(cols, dtype=torch.float32, device=part2d.device)
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=part2d.device)
     _ck(lib.slak_colsum_f32(_p(part2d), rows, cols, _p(out), st), "slak_colsum_f32")
     ops._count(1)
     return out
@@ -105,29 +106,43 @@ class FusedBlockFunction(torch.autograd.Function):
         training = cfg["training"]
         sync = cfg["sync_bn"]
         if training:
-            # [C][6] sums, then one extra slot: this rank's element count per channel (SyncBN all-reduces both)
-            sums_buf = torch.empty((C * 6 + 1,), dtype=torch.float64, device=dev)
+            count = float(N * HW)
+            count_dev = None
+            dist, world = _dist_world(cfg["process_group"]) if sync else (None, 1)
+            ex = syncbn.get(cfg["process_group"], dev) if world > 1 else None
+            # [C][6] sums, then this rank's element count per channel (SyncBN sums both over the ranks: ranks may hold
+            # different batch sizes, torch/nn/modules/_functions.py:33-60), then the global count (peer-memory path)
+            if ex is not None:
+                sums_buf = ex.slot(cfg["sites"][0], C * 6 + 2, torch.float64)        # lives in the symmetric buffer
+            else:
+                sums_buf = torch.empty((C * 6 + 2,), dtype=torch.float64, device=dev)
             sums = sums_buf[:C * 6]
             need = lib.slak_block_conv_fwd_workspace(N, C, H, W)
             ws = ops._workspace(need, dev)
             with ops.timed("dw_fwd", (N, C, H, W, KL)):
                 _ck(lib.slak_block_conv_fwd(_p(xb), _p(w1), _p(w2), _p(w3), _p(y1), _p(y2), _p(y3), _p(sums), _p(ws),
                                             ws.numel(), N, C, H, W, KL, st), "slak_block_conv_fwd")
-            count = float(N * HW)
-            count_dev = None
-            dist, world = _dist_world(cfg["process_group"]) if sync else (None, 1)
-            if world > 1:                     # SyncBatchNorm: statistics over the global batch
-                # the true per-rank counts are summed with the statistics (ranks may hold different batch sizes,
-                # torch/nn/modules/_functions.py:33-60) and stay on the device: no host round trip, graph-capturable
-                sums_buf[C * 6:].fill_(count)
-                dist.all_reduce(sums_buf, group=cfg["process_group"])
-                count_dev = sums_buf[C * 6:]
             mean = torch.empty((3, C), dtype=torch.float32, device=dev)
             istd = torch.empty((3, C), dtype=torch.float32, device=dev)
             rm, rv = cfg["running_mean"], cfg["running_var"]
-            _ck(lib.slak_bn3_finalize_fwd(_p(sums), count, _p(count_dev), _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3), _ptr3(*rm),
-                                          _ptr3(*rv), cfg["bn_eps"], cfg["bn_momentum"], C, _p(scale), _p(shift),
-                                          _p(mean), _p(istd), st), "slak_bn3_finalize_fwd")
+            if ex is not None:
+                # SyncBatchNorm, exchange fused into the finalize kernel: one-shot all-reduce over NVLink peer memory
+                site = cfg["sites"][0]
+                sums_buf[C * 6:C * 6 + 1].fill_(count)
+                _ck(lib.slak_bn3_finalize_fwd_sync(ex.ptrs, ex.slot_off(site), ex.flag_off(site), ex.rank, ex.world,
+                                                   ex.epoch_ptr(site), _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3), _ptr3(*rm),
+                                                   _ptr3(*rv), cfg["bn_eps"], cfg["bn_momentum"], C, _p(scale), _p(shift),
+                                                   _p(mean), _p(istd), st), "slak_bn3_finalize_fwd_sync")
+                count_dev = sums_buf[C * 6 + 1:]          # the global count, written by the kernel
+                ops._count(1)
+            else:
+                if world > 1:                 # SyncBatchNorm over NCCL: statistics and counts of the global batch
+                    sums_buf[C * 6:C * 6 + 1].fill_(count)
+                    dist.all_reduce(sums_buf[:C * 6 + 1], group=cfg["process_group"])
+                    count_dev = sums_buf[C * 6:C * 6 + 1]
+                _ck(lib.slak_bn3_finalize_fwd(_p(sums), count, _p(count_dev), _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3),
+                                              _ptr3(*rm), _ptr3(*rv), cfg["bn_eps"], cfg["bn_momentum"], C, _p(scale),
+                                              _p(shift), _p(mean), _p(istd), st), "slak_bn3_finalize_fwd")
             for nbt in cfg["num_batches_tracked"]:
                 if nbt is not None:
                     nbt.add_(1)
@@ -266,23 +281,34 @@ class FusedBlockFunction(torch.autograd.Function):
         part = torch.empty((parts, 6, C), dtype=torch.float32, device=dev)
         _ck(lib.slak_bn3_sum_ln_bwd(_p(dxn), _p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(mu), _p(rstd),
                                     _p(du), _p(part), N, C, HW, st), "slak_bn3_sum_ln_bwd")
-        red = _colsum(lib, part.view(parts, 6 * C), st).view(6, C)
-        dlnw, dlnb = red[0], red[1]
-        S = red[2:6].contiguous()
-        S_local = None
-        if cfg["sync_bn"]:
-            dist, world = _dist_world(cfg["process_group"])
+        coef = torch.empty((9, C), dtype=torch.float32, device=dev)
+        dbnw = torch.empty((3, C), dtype=torch.float32, device=dev)
+        dbnb = torch.empty((3, C), dtype=torch.float32, device=dev)
+        dist, world = _dist_world(cfg["process_group"]) if cfg["sync_bn"] else (None, 1)
+        ex = syncbn.get(cfg["process_group"], dev) if world > 1 else None
+        if ex is not None:
+            # the fold writes [dlnw, dlnb, S(4 x C)] straight into this site's slot of the symmetric buffer; the finalize
+            # kernel exchanges S with the peers (global sums for dy, this rank's own sums for the BN parameter gradients,
+            # as torch's SyncBatchNorm: its all-reduce comes after grad_weight / grad_bias)
+            site = cfg["sites"][1]
+            red = _colsum(lib, part.view(parts, 6 * C), st, out=ex.slot(site, 6 * C, torch.float32)).view(6, C)
+            dlnw, dlnb = red[0].clone(), red[1].clone()
+            _ck(lib.slak_bn3_finalize_bwd_sync(ex.ptrs, ex.slot_off(site) + 2 * C * 4, ex.flag_off(site), ex.rank, ex.world,
+                                               ex.epoch_ptr(site), _p(ctx.count_dev), _ptr3(bw1, bw2, bw3), _p(mean), _p(istd),
+                                               C, _p(coef), _p(dbnw), _p(dbnb), st), "slak_bn3_finalize_bwd_sync")
+        else:
+            red = _colsum(lib, part.view(parts, 6 * C), st).view(6, C)
+            dlnw, dlnb = red[0], red[1]
+            S = red[2:6].contiguous()
+            S_local = None
             if world > 1:
                 # dy needs the GLOBAL sums; the BN weight / bias gradients are taken from this rank's own sums, as
                 # torch's SyncBatchNorm does (its all-reduce comes after grad_weight / grad_bias), so that the
                 # data-parallel gradient average gives global_sum / world and not the global sum itself
                 S_local = S.clone()
                 dist.all_reduce(S, group=cfg["process_group"])
-        coef = torch.empty((9, C), dtype=torch.float32, device=dev)
-        dbnw = torch.empty((3, C), dtype=torch.float32, device=dev)
-        dbnb = torch.empty((3, C), dtype=torch.float32, device=dev)
-        _ck(lib.slak_bn3_finalize_bwd(_p(S), _p(S_local), ctx.count, _p(ctx.count_dev), _ptr3(bw1, bw2, bw3), _p(mean), _p(istd), C, _p(coef),
-                                      _p(dbnw), _p(dbnb), st), "slak_bn3_finalize_bwd")
+            _ck(lib.slak_bn3_finalize_bwd(_p(S), _p(S_local), ctx.count, _p(ctx.count_dev), _ptr3(bw1, bw2, bw3),
+                                          _p(mean), _p(istd), C, _p(coef), _p(dbnw), _p(dbnb), st), "slak_bn3_finalize_bwd")
         dy1, dy2, dy3 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
         _ck(lib.slak_bn3_bwd_apply(_p(du), _p(y1), _p(y2), _p(y3), _p(coef), _p(dy1), _p(dy2), _p(dy3), N, C, HW, st),
             "slak_bn3_bwd_apply")
@@ -345,6 +371,20 @@ class _Shape:
         self.dtype = torch.bfloat16
 
 
+def _sync_sites(block, group, device):
+    """(forward site, backward site) of this Block in the peer-memory exchange: assigned at first use, in execution order,
+    which is the same on every rank."""
+    _, world = _dist_world(group)
+    if world <= 1:
+        return None
+    ex = syncbn.get(group, device)
+    if ex is None:
+        return None
+    if getattr(block, "_slak_sync_sites", None) is None:
+        block._slak_sync_sites = (ex.new_site(), ex.new_site())
+    return block._slak_sync_sites
+
+
 def fused_block_forward(block, x):
     lk = block.large_kernel
     if hasattr(lk, "lkb_reparam_v"):
@@ -360,8 +400,11 @@ def fused_block_forward(block, x):
     sync = isinstance(bns[0], torch.nn.SyncBatchNorm)
     track = all(bn.track_running_stats and bn.running_mean is not None for bn in bns)
     training = block.training or not track
+    if sync and not hasattr(block, "_slak_sync_sites"):
+        block._slak_sync_sites = None
     cfg = {
         "training": training, "sync_bn": sync, "process_group": getattr(bns[0], "process_group", None) if sync else None,
+        "sites": _sync_sites(block, getattr(bns[0], "process_group", None), x.device) if (sync and training) else None,
         "bn_eps": float(bns[0].eps), "bn_momentum": float(bns[0].momentum),
         "ln_eps": float(block.norm.eps),
         "running_mean": tuple(bn.running_mean if (track and block.training) or not training else None for bn in bns),

@@ -561,18 +561,15 @@ __global__ void bn3_reduce_partials_kernel(const float* __restrict__ part, int s
 // out: scale[3][C], shift[C], mean[3][C], istd[3][C]
 struct P3 { const float* p[3]; };
 struct M3 { float* p[3]; };
-__global__ void bn3_finalize_fwd_kernel(const double* __restrict__ sums, double count, const double* __restrict__ count_dev,
-                                        P3 bnw, P3 bnb, M3 rmean, M3 rvar,
-                                        float eps, float momentum, int C, float* __restrict__ scale,
-                                        float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ istd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (count_dev) count = *count_dev;            // SyncBN: the all-reduced number of elements per channel
+__device__ __forceinline__ void bn3_finalize_fwd_channel(const double* s6, double count, int c, const P3& bnw, const P3& bnb,
+                                                         const M3& rmean, const M3& rvar, float eps, float momentum, int C,
+                                                         float* __restrict__ scale, float* __restrict__ shift,
+                                                         float* __restrict__ mean, float* __restrict__ istd) {
   float sh = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double m = sums[c * 6 + 2 * i] / count;
-    double var = sums[c * 6 + 2 * i + 1] / count - m * m;
+    const double m = s6[2 * i] / count;
+    double var = s6[2 * i + 1] / count - m * m;
     if (var < 0.0) var = 0.0;
     const float is = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = bnw.p[i][c] * is;
@@ -588,6 +585,72 @@ __global__ void bn3_finalize_fwd_kernel(const double* __restrict__ sums, double 
   }
   shift[c] = sh;
 }
+__global__ void bn3_finalize_fwd_kernel(const double* __restrict__ sums, double count, const double* __restrict__ count_dev,
+                                        P3 bnw, P3 bnb, M3 rmean, M3 rvar,
+                                        float eps, float momentum, int C, float* __restrict__ scale,
+                                        float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ istd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (count_dev) count = *count_dev;            // SyncBN: the all-reduced number of elements per channel
+  double s6[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s6[k] = sums[c * 6 + k];
+  bn3_finalize_fwd_channel(s6, count, c, bnw, bnb, rmean, rvar, eps, momentum, C, scale, shift, mean, istd);
+}
+
+// ---- SyncBatchNorm statistics exchange fused into the finalize kernels: one-shot all-reduce over NVLink peer memory --------
+// Every rank holds a SYMMETRIC buffer (same layout on all ranks, mapped into every peer's address space: torch's
+// symmetric-memory allocator supplies the memory and the peer pointers, the exchange is this kernel).  A rank's
+// payload for this call site sits at `slot_off`; `flag_off` addresses a row of `world` 32-bit flags for the site.
+//   1. block 0 stores the site's epoch into flag[my rank] of every peer (release, system scope): "my payload is written"
+//      (it was written by earlier kernels on this stream);
+//   2. every block waits until its own flag row shows the epoch from every rank (acquire, system scope);
+//   3. every thread reads its channel's values from all ranks through the peer pointers (fixed rank order: the sums are
+//      bitwise identical on all ranks) and runs the BatchNorm finalize on them.
+// Two ranks can be at most one call site apart (a rank passes site s + 1 only after every peer has signalled it, which a
+// peer does after its site-s kernel finished), so per-site slots are never overwritten while a peer still reads them.
+// The epoch lives on the device (one counter per site, bumped by a 1-thread kernel right after) -> CUDA-graph replayable.
+constexpr int kMaxPeers = 8;
+struct PeerTable { const uint8_t* base[kMaxPeers]; };
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ double ld_sys_f64(const double* p) { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ float ld_sys_f32(const float* p) { float v; asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
+
+__device__ __forceinline__ void peer_signal_and_wait(const PeerTable& pt, size_t flag_off, int rank, int world, uint32_t epoch) {
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(pt.base[threadIdx.x]) + flag_off) + rank, epoch);
+  }
+  if (threadIdx.x < world) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(pt.base[rank] + flag_off) + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      if (clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a peer died; fail loudly instead of hanging the GPU
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void bn3_finalize_fwd_sync_kernel(PeerTable pt, size_t slot_off, size_t flag_off, int rank, int world,
+                                             const uint32_t* __restrict__ epoch_dev, P3 bnw, P3 bnb, M3 rmean, M3 rvar,
+                                             float eps, float momentum, int C, float* __restrict__ scale,
+                                             float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ istd) {
+  peer_signal_and_wait(pt, flag_off, rank, world, *epoch_dev + 1u);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, count = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const double* ps = reinterpret_cast<const double*>(pt.base[r] + slot_off);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s6[k] += ld_sys_f64(ps + c * 6 + k);
+    count += ld_sys_f64(ps + C * 6);
+  }
+  bn3_finalize_fwd_channel(s6, count, c, bnw, bnb, rmean, rvar, eps, momentum, C, scale, shift, mean, istd);
+  if (c == 0) const_cast<double*>(reinterpret_cast<const double*>(pt.base[rank] + slot_off))[C * 6 + 1] = count;   // for backward
+}
+__global__ void epoch_bump_kernel(uint32_t* e) { *e += 1u; }
+
 // eval mode: scale/shift from the running statistics
 __global__ void bn3_eval_affine_kernel(P3 bnw, P3 bnb, P3 rmean, P3 rvar, float eps, int C,
                                        float* __restrict__ scale, float* __restrict__ shift) {
@@ -606,6 +669,24 @@ __global__ void bn3_eval_affine_kernel(P3 bnw, P3 bnb, P3 rmean, P3 rvar, float 
 // S_local (may be NULL = S): this rank's own sums.  The parameter gradients come from them, as torch's SyncBatchNorm
 // takes grad_weight / grad_bias before its all-reduce (torch/nn/modules/_functions.py:140-160) and leaves their
 // averaging to the data-parallel wrapper; the dy coefficients need the global sums.
+__device__ __forceinline__ void bn3_finalize_bwd_channel(const double* Sg, const double* Sl, double count, int c, const P3& bnw,
+                                                         const float* __restrict__ mean, const float* __restrict__ istd, int C,
+                                                         float* __restrict__ coef, float* __restrict__ dbnw,
+                                                         float* __restrict__ dbnb) {
+  const double S0 = Sg[0], L0 = Sl[0];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double m = mean[i * C + c], is = istd[i * C + c], w = bnw.p[i][c];
+    const double Si = Sg[i + 1];
+    const double D = is * (Si - m * S0);            // sum du * yhat_i
+    const double a = w * is;
+    coef[i * C + c] = (float)a;
+    coef[(3 + i) * C + c] = (float)(-a * is * D / count);
+    coef[(6 + i) * C + c] = (float)(-a * S0 / count + a * is * m * D / count);
+    dbnw[i * C + c] = (float)(is * (Sl[i + 1] - m * L0));
+    dbnb[i * C + c] = (float)L0;
+  }
+}
 __global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, const float* __restrict__ S_local, double count,
                                         const double* __restrict__ count_dev, P3 bnw,
                                         const float* __restrict__ mean, const float* __restrict__ istd, int C,
@@ -614,19 +695,30 @@ __global__ void bn3_finalize_bwd_kernel(const float* __restrict__ S, const float
   if (c >= C) return;
   if (count_dev) count = *count_dev;
   if (!S_local) S_local = S;
-  const double S0 = S[c], L0 = S_local[c];
+  double Sg[4], Sl[4];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double m = mean[i * C + c], is = istd[i * C + c], w = bnw.p[i][c];
-    const double Si = S[(i + 1) * C + c];
-    const double D = is * (Si - m * S0);            // sum du * yhat_i
-    const double a = w * is;
-    coef[i * C + c] = (float)a;
-    coef[(3 + i) * C + c] = (float)(-a * is * D / count);
-    coef[(6 + i) * C + c] = (float)(-a * S0 / count + a * is * m * D / count);
-    dbnw[i * C + c] = (float)(is * ((double)S_local[(i + 1) * C + c] - m * L0));
-    dbnb[i * C + c] = (float)L0;
+  for (int k = 0; k < 4; ++k) { Sg[k] = S[k * C + c]; Sl[k] = S_local[k * C + c]; }
+  bn3_finalize_bwd_channel(Sg, Sl, count, c, bnw, mean, istd, C, coef, dbnw, dbnb);
+}
+// the same with the one-shot NVLink exchange of S (float [4][C] at slot_off of every rank's symmetric buffer)
+__global__ void bn3_finalize_bwd_sync_kernel(PeerTable pt, size_t slot_off, size_t flag_off, int rank, int world,
+                                             const uint32_t* __restrict__ epoch_dev, const double* __restrict__ count_dev,
+                                             P3 bnw, const float* __restrict__ mean, const float* __restrict__ istd, int C,
+                                             float* __restrict__ coef, float* __restrict__ dbnw, float* __restrict__ dbnb) {
+  peer_signal_and_wait(pt, flag_off, rank, world, *epoch_dev + 1u);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double Sg[4] = {0.0, 0.0, 0.0, 0.0}, Sl[4];
+  for (int r = 0; r < world; ++r) {
+    const float* ps = reinterpret_cast<const float*>(pt.base[r] + slot_off);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = ld_sys_f32(ps + k * C + c);
+      Sg[k] += (double)v;
+      if (r == rank) Sl[k] = (double)v;
+    }
   }
+  bn3_finalize_bwd_channel(Sg, Sl, *count_dev, c, bnw, mean, istd, C, coef, dbnw, dbnb);
 }
 
 // out[c] = sum_r part[r][c], rows added in a fixed order (the per-CTA partial rows of the kernels above)
@@ -762,6 +854,38 @@ int bn3_finalize_fwd(const double* sums, double count, const double* count_dev, 
   P3 w{{bnw[0], bnw[1], bnw[2]}}, b{{bnb[0], bnb[1], bnb[2]}};
   M3 rm{{rmean[0], rmean[1], rmean[2]}}, rv{{rvar[0], rvar[1], rvar[2]}};
   bn3_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, count, count_dev, w, b, rm, rv, eps, momentum, C, scale, shift, mean, istd);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+static int fill_peers(PeerTable* pt, const void* const* peers, int world) {
+  SLAK_REQUIRE(world >= 2 && world <= kMaxPeers, SLAK_ERR_UNSUPPORTED, "world size %d outside 2..%d", world, kMaxPeers);
+  for (int r = 0; r < kMaxPeers; ++r) pt->base[r] = r < world ? (const uint8_t*)peers[r] : nullptr;
+  return SLAK_OK;
+}
+int bn3_finalize_fwd_sync(const void* const* peers, size_t slot_off, size_t flag_off, int rank, int world, uint32_t* epoch_dev,
+                          const float* const* bnw, const float* const* bnb, float* const* rmean, float* const* rvar, float eps,
+                          float momentum, int C, float* scale, float* shift, float* mean, float* istd, cudaStream_t st) {
+  PeerTable pt;
+  int rc = fill_peers(&pt, peers, world);
+  if (rc) return rc;
+  P3 w{{bnw[0], bnw[1], bnw[2]}}, b{{bnb[0], bnb[1], bnb[2]}};
+  M3 rm{{rmean[0], rmean[1], rmean[2]}}, rv{{rvar[0], rvar[1], rvar[2]}};
+  bn3_finalize_fwd_sync_kernel<<<(C + 127) / 128, 128, 0, st>>>(pt, slot_off, flag_off, rank, world, epoch_dev, w, b, rm, rv, eps,
+                                                               momentum, C, scale, shift, mean, istd);
+  epoch_bump_kernel<<<1, 1, 0, st>>>(epoch_dev);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+int bn3_finalize_bwd_sync(const void* const* peers, size_t slot_off, size_t flag_off, int rank, int world, uint32_t* epoch_dev,
+                          const double* count_dev, const float* const* bnw, const float* mean, const float* istd, int C,
+                          float* coef, float* dbnw, float* dbnb, cudaStream_t st) {
+  PeerTable pt;
+  int rc = fill_peers(&pt, peers, world);
+  if (rc) return rc;
+  P3 w{{bnw[0], bnw[1], bnw[2]}};
+  bn3_finalize_bwd_sync_kernel<<<(C + 127) / 128, 128, 0, st>>>(pt, slot_off, flag_off, rank, world, epoch_dev, count_dev, w, mean,
+                                                               istd, C, coef, dbnw, dbnb);
+  epoch_bump_kernel<<<1, 1, 0, st>>>(epoch_dev);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }

@@ -49,6 +49,12 @@ int bn3_finalize_fwd(const double* sums, double count, const double* count_dev, 
                      float* mean, float* istd, cudaStream_t st);
 int bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean, const float* const* rvar,
                     float eps, int C, float* scale, float* shift, cudaStream_t st);
+int bn3_finalize_fwd_sync(const void* const* peers, size_t slot_off, size_t flag_off, int rank, int world, uint32_t* epoch_dev,
+                          const float* const* bnw, const float* const* bnb, float* const* rmean, float* const* rvar, float eps,
+                          float momentum, int C, float* scale, float* shift, float* mean, float* istd, cudaStream_t st);
+int bn3_finalize_bwd_sync(const void* const* peers, size_t slot_off, size_t flag_off, int rank, int world, uint32_t* epoch_dev,
+                          const double* count_dev, const float* const* bnw, const float* mean, const float* istd, int C,
+                          float* coef, float* dbnw, float* dbnb, cudaStream_t st);
 int bn3_finalize_bwd(const float* S, const float* S_local, double count, const double* count_dev, const float* const* bnw, const float* mean, const float* istd, int C,
                      float* coef, float* dbnw, float* dbnb, cudaStream_t st);
 int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, const float* shift,
@@ -311,6 +317,27 @@ SLAK_API int slak_bn3_finalize_fwd(const double* sums, double count, const doubl
   SLAK_REQUIRE(sums && bnw && bnb && rmean && rvar && scale && shift && mean && istd && C > 0 && (count > 0 || count_dev), SLAK_ERR_BAD_ARG, "bad argument");
   for (int i = 0; i < 3; ++i) SLAK_REQUIRE(bnw[i] && bnb[i], SLAK_ERR_BAD_ARG, "null BN parameter");
   return blk::bn3_finalize_fwd(sums, count, count_dev, bnw, bnb, rmean, rvar, eps, momentum, C, scale, shift, mean, istd, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_finalize_fwd_sync(const void* const* peer_bases, size_t slot_off, size_t flag_off, int rank, int world,
+                                        uint32_t* epoch_dev, const float* const* bnw, const float* const* bnb,
+                                        float* const* rmean, float* const* rvar, float eps, float momentum, int C, float* scale,
+                                        float* shift, float* mean, float* istd, void* stream) {
+  SLAK_REQUIRE(peer_bases && epoch_dev && bnw && bnb && rmean && rvar && scale && shift && mean && istd && C > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  SLAK_REQUIRE(rank >= 0 && rank < world, SLAK_ERR_BAD_ARG, "rank %d outside world %d", rank, world);
+  for (int i = 0; i < 3; ++i) SLAK_REQUIRE(bnw[i] && bnb[i], SLAK_ERR_BAD_ARG, "null BN parameter");
+  return blk::bn3_finalize_fwd_sync(peer_bases, slot_off, flag_off, rank, world, epoch_dev, bnw, bnb, rmean, rvar, eps, momentum, C,
+                                    scale, shift, mean, istd, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_bn3_finalize_bwd_sync(const void* const* peer_bases, size_t slot_off, size_t flag_off, int rank, int world,
+                                        uint32_t* epoch_dev, const double* count_dev, const float* const* bnw, const float* mean,
+                                        const float* istd, int C, float* coef, float* dbnw, float* dbnb, void* stream) {
+  SLAK_REQUIRE(peer_bases && epoch_dev && count_dev && bnw && bnw[0] && bnw[1] && bnw[2] && mean && istd && coef && dbnw && dbnb && C > 0,
+               SLAK_ERR_BAD_ARG, "bad argument");
+  SLAK_REQUIRE(rank >= 0 && rank < world, SLAK_ERR_BAD_ARG, "rank %d outside world %d", rank, world);
+  return blk::bn3_finalize_bwd_sync(peer_bases, slot_off, flag_off, rank, world, epoch_dev, count_dev, bnw, mean, istd, C, coef,
+                                    dbnw, dbnb, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_bn3_eval_affine(const float* const* bnw, const float* const* bnb, const float* const* rmean,

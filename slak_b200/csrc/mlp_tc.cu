@@ -34,13 +34,17 @@ constexpr int kBox = 64 * 128;                  // one 64-row x 128-byte TMA box
 constexpr int kThreads = 384;
 enum Epi { EPI_FC1 = 0, EPI_BIAS = 1, EPI_DGELU = 2, EPI_PLAIN = 3 };
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 256 ? 3 : 4;
+template <int BN, int EPI> struct Cfg {
+  // DGELU brings the saved pre-activation H in by TMA into a third staging slab per group (it is overwritten in place by
+  // dH), and pays for that with one operand stage less: its main loop (K = C <= 768) is short next to its epilogue
+  static constexpr bool kDgelu = (EPI == EPI_DGELU);
+  static constexpr int kStages = (BN == 256 ? 3 : 4) - (kDgelu ? 1 : 0);
   static constexpr int kATile = 2 * kBox;                      // 128 rows x 64 k
   static constexpr int kBTile = (BN / 64) * kBox;
   static constexpr int kStage = kATile + kBTile;
-  static constexpr int kOffStg = kStages * kStage;             // staging: [group][2] slabs of 128 rows x 128 B
-  static constexpr int kOffCol = kOffStg + 4 * 2 * kBox;       // DGELU: per-CTA column accumulators [N <= 3072] fp32 + scratch
+  static constexpr int kSlabs = kDgelu ? 3 : 2;                // staging slabs (128 rows x 128 B) per epilogue group
+  static constexpr int kOffStg = kStages * kStage;
+  static constexpr int kOffCol = kOffStg + 2 * kSlabs * 2 * kBox;   // DGELU: per-CTA column accumulators [N <= 3072] fp32 + scratch
   static constexpr int kColBytes = 3072 * 4 + 8 * 64 * 4;
   static constexpr int kOffBar = kOffCol + kColBytes;
   static constexpr int kSmem = kOffBar + 256 + 1024;
@@ -109,7 +113,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                    const __grid_constant__ CUtensorMap o0map, const __grid_constant__ CUtensorMap o1map, Params P) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -122,7 +126,7 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   const int KB = (P.K + BK - 1) / BK;
   const int ksteps_last = ((P.K - (KB - 1) * BK) + 15) / 16;     // k16 steps of the last (partial) K block
 
-  constexpr int B_FULL = 0, B_EMPTY = kStages, B_ACC_FULL = 2 * kStages, B_ACC_EMPTY = B_ACC_FULL + 2;
+  constexpr int B_FULL = 0, B_EMPTY = kStages, B_ACC_FULL = 2 * kStages, B_ACC_EMPTY = B_ACC_FULL + 2, B_H_FULL = B_ACC_EMPTY + 2;
   const uint32_t bar0 = base + C::kOffBar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::kOffBar + 192);
@@ -130,9 +134,10 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(BAR(B_ACC_FULL + a), 1); mbar_init(BAR(B_ACC_EMPTY + a), 8); }
+    for (int hb = 0; hb < 6; ++hb) mbar_init(BAR(B_H_FULL + hb), 1);     // DGELU: H slab landed (group g, slab b: index 3 g + b)
     mbar_fence_init();
     tma_prefetch_desc(&amap); tma_prefetch_desc(&bmap); tma_prefetch_desc(&o0map);
-    if (EPI == EPI_FC1) tma_prefetch_desc(&o1map);
+    if (EPI == EPI_FC1 || EPI == EPI_DGELU) tma_prefetch_desc(&o1map);
   }
   if (EPI == EPI_DGELU) {   // column accumulators start at zero
     float* col = reinterpret_cast<float*>(sm + C::kOffCol);
@@ -194,30 +199,37 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     const int g = (warp - 4) >> 2, e = (warp - 4) & 3;
     const int L = e * 32 + lane;                          // row of the tile = TMEM lane
     const int nb = 1 + g;                                 // named barrier of the group
-    uint8_t* stg = sm + C::kOffStg + g * 2 * kBox * 2;     // two slabs [128 rows][128 B] swizzled (each = two 64-row boxes)
-    const uint32_t stg_s = base + C::kOffStg + g * 2 * kBox * 2;
+    uint8_t* stg = sm + C::kOffStg + g * C::kSlabs * 2 * kBox;   // kSlabs slabs [128 rows][128 B] swizzled (each = two 64-row boxes)
+    const uint32_t stg_s = base + C::kOffStg + g * C::kSlabs * 2 * kBox;
     float* col = reinterpret_cast<float*>(sm + C::kOffCol);
     float* scratch = col + 3072;                          // [8 warps][64]
     float* bias_s = col + g * 64;                         // FC1 / BIAS: the group's rounded bias slab (col[] is DGELU's)
     int it = 0, slab_ctr = 0;
+    // DGELU: the saved pre-activation H of a slab arrives by TMA (o1map is H's map) in the staging slab where dH is then
+    // formed in place; the elected thread runs a prefetch cursor two slabs ahead of the compute (three slabs rotate)
+    int pf_t = blockIdx.x, pf_sl = 0, pf_count = 0;
+    auto pf_issue = [&]() {
+      while (pf_t < tiles && (pf_t % n_tiles) * BN + 64 * (g * SPG + pf_sl) >= P.N)
+        if (++pf_sl == SPG) { pf_sl = 0; pf_t += gridDim.x; }
+      if (pf_t >= tiles) return;
+      const int b = pf_count % 3;
+      const int pm0 = (pf_t / n_tiles) * BM, pn0 = (pf_t % n_tiles) * BN + 64 * (g * SPG + pf_sl);
+      const uint32_t bar = BAR(B_H_FULL + 3 * g + b), dst = stg_s + b * 2 * kBox;
+      mbar_expect_tx(bar, 2 * kBox);
+      tma_load_3d(dst, &o1map, bar, pn0, pm0, 0);
+      tma_load_3d(dst + kBox, &o1map, bar, pn0, pm0 + 64, 0);
+      ++pf_count;
+      if (++pf_sl == SPG) { pf_sl = 0; pf_t += gridDim.x; }
+    };
+    if constexpr (EPI == EPI_DGELU) {
+      if (e == 0 && lane == 0) { pf_issue(); pf_issue(); }
+    }
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int m0 = (t / n_tiles) * BM, nt0 = (t % n_tiles) * BN;
       const int ab = it & 1, aph = (it >> 1) & 1;
       const int m = m0 + L;
-      if constexpr (EPI == EPI_DGELU) {
-        // pull this thread's H row segments of the CTA's NEXT tile into L2 (one 128-byte line per 64-column slab), so that
-        // the row-per-thread loads below see L2 latency instead of HBM latency
-        const int tn = t + gridDim.x;
-        if (tn < tiles) {
-          const int mn = (tn / n_tiles) * BM + L, nn = (tn % n_tiles) * BN + 64 * g * SPG;
-          if (mn < P.M)
-#pragma unroll
-            for (int q = 0; q < SPG; ++q)
-              if (nn + 64 * q < P.N) prefetch_l2(P.h + (size_t)mn * P.N + nn + 64 * q);
-        }
-      }
 #pragma unroll 1
-      for (int sl = 0; sl < SPG; ++sl, ++slab_ctr) {
+      for (int sl = 0; sl < SPG; ++sl) {
         const int n0 = nt0 + 64 * (g * SPG + sl);         // first column of the slab
         if (n0 >= P.N) {                                  // slab entirely beyond N (narrow N in a wide tile)
           if (sl == SPG - 1) {
@@ -227,12 +239,6 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));
           }
           continue;
-        }
-        uint4 hraw[8];                                    // DGELU: the saved pre-activation row, requested before the wait
-        if constexpr (EPI == EPI_DGELU) {
-          const uint4* hp = reinterpret_cast<const uint4*>(P.h + (size_t)(m < P.M ? m : 0) * P.N + n0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) hraw[j] = (n0 + 8 * j < P.N) ? __ldg(hp + j) : make_uint4(0, 0, 0, 0);
         }
         if (sl == 0) { mbar_wait(BAR(B_ACC_FULL + ab), aph); tc_fence_after(); }
         uint32_t v[64];
@@ -247,8 +253,12 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         // staging: the single-output epilogues alternate between the group's two slabs; FC1 writes H to slab 0 and A to
         // slab 1 and stores them as separate bulk groups.  Either way a slab is rewritten one slab period after its
         // store was issued, and only the store issued before the most recent one has to have finished reading.
-        const int buf = (EPI == EPI_FC1) ? 0 : (slab_ctr & 1);
-        if (e == 0 && lane == 0) bulk_wait_group_read<1>();
+        const int buf = (EPI == EPI_FC1) ? 0 : (EPI == EPI_DGELU ? slab_ctr % 3 : (slab_ctr & 1));
+        if constexpr (EPI == EPI_DGELU) {
+          mbar_wait(BAR(B_H_FULL + 3 * g + buf), (slab_ctr / 3) & 1);       // H of this slab landed in slab `buf`
+        } else {
+          if (e == 0 && lane == 0) bulk_wait_group_read<1>();
+        }
         if constexpr (EPI == EPI_FC1 || EPI == EPI_BIAS) {
           // the slab's 64 bias values, rounded to bf16 once (b.to(bf16) of the module path), for broadcast reads below;
           // the previous slab's readers are past the barrier that closed it
@@ -257,7 +267,7 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             bias_s[c] = (n0 + c < P.N) ? __bfloat162float(__float2bfloat16_rn(__ldg(P.bias + n0 + c))) : 0.f;
           }
         }
-        named_bar_sync(nb, 128);
+        if constexpr (EPI != EPI_DGELU) named_bar_sync(nb, 128);
         uint8_t* s0 = stg + buf * 2 * kBox;
         uint8_t* s1 = stg + 2 * kBox;
         if constexpr (EPI == EPI_FC1) {
@@ -306,7 +316,8 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
 #pragma unroll
               for (int k = 0; k < 4; ++k) ob[k] = pack2(add2(mk2u(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]), bb[k]));
             } else if constexpr (EPI == EPI_DGELU) {
-              const uint32_t hb[4] = {hraw[j].x, hraw[j].y, hraw[j].z, hraw[j].w};
+              const uint4 hq = *reinterpret_cast<const uint4*>(s0 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4));   // H, replaced by dH below
+              const uint32_t hb[4] = {hq.x, hq.y, hq.z, hq.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 ob[k] = pack2(mul2(mk2u(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]), dgelu2(unpack2(hb[k]))));
@@ -353,7 +364,12 @@ mlp_gemm_nt_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             tma_store_3d(&o0map, a0 + kBox, n0, m0 + 64, 0);
           }
           bulk_commit_group();
+          if constexpr (EPI == EPI_DGELU) {
+            bulk_wait_group_read<1>();      // the store before this one has let go of its slab: H of slab + 2 goes there
+            pf_issue();
+          }
         }
+        ++slab_ctr;                         // counts the slabs actually processed (skipped ones take no staging slab)
       }
     }
     if (e == 0 && lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last tile store
@@ -516,8 +532,8 @@ template <int BN, int EPI>
 static int launch_nt(const CUtensorMap& am, const CUtensorMap& bm, const CUtensorMap& o0, const CUtensorMap& o1,
                      const Params& P, int grid, cudaStream_t st) {
   auto kern = mlp_gemm_nt_kernel<BN, EPI>;
-  SLAK_SET_MAX_SMEM(kern, Cfg<BN>::kSmem);
-  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(am, bm, o0, o1, P);
+  SLAK_SET_MAX_SMEM(kern, (Cfg<BN, EPI>::kSmem));
+  kern<<<grid, kThreads, Cfg<BN, EPI>::kSmem, st>>>(am, bm, o0, o1, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
@@ -535,7 +551,7 @@ int mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const 
   if ((rc = make_plane_map(&am, a, 1, 1, M, K))) return rc;
   if ((rc = make_plane_map(&bm, b, 1, 1, N, K))) return rc;
   if ((rc = make_plane_map(&o0, out0 ? out0 : out1, 1, 1, M, N))) return rc;
-  if ((rc = make_plane_map(&o1, out1 ? out1 : out0, 1, 1, M, N))) return rc;
+  if ((rc = make_plane_map(&o1, epi == EPI_DGELU ? aux_h : (out1 ? out1 : out0), 1, 1, M, N))) return rc;   // DGELU: H's map
   Params P{};
   P.bias = bias; P.h = (const __nv_bfloat16*)aux_h; P.colpart = colpart; P.M = M; P.N = N; P.K = K;
   P.write_h = out0 != nullptr;

@@ -21,36 +21,50 @@ import torch
 import torch.distributed as dist
 
 
-class GradientAllReducer:
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, process_group=None, broadcast: bool = True):
-        if not (dist.is_available() and dist.is_initialized()):
-            raise RuntimeError("GradientAllReducer needs an initialised torch.distributed process group")
-        self.group = process_group
-        self.world = dist.get_world_size(process_group)
+class FlatGradients:
+    """All gradients of a module as views of ONE flat buffer laid out in reverse parameter order (the order backward
+    produces them): static addresses (CUDA-graph capture, pointer tables of the fused optimizer), one-pass zeroing."""
+
+    def __init__(self, module: torch.nn.Module):
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
         if any(p.device != dev or p.dtype != dt for p in self.params):
             raise ValueError("all parameters must share one device and dtype (fp32 master weights)")
+        self.order = list(reversed(self.params))
+        self.offs, total = [], 0
+        for p in self.order:
+            self.offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        for p, o in zip(self.order, self.offs):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+
+    def zero_grad(self) -> None:
+        """Gradients stay views of the flat buffer: zero it in one pass (instead of optimizer.zero_grad())."""
+        self.flat.zero_()
+
+
+class GradientAllReducer(FlatGradients):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 25.0, process_group=None, broadcast: bool = True):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("GradientAllReducer needs an initialised torch.distributed process group")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
         if broadcast:                      # identical initial weights and buffers on every rank (DDP's constructor)
             with torch.no_grad():
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group else 0,
                                    group=process_group)
-        # flat gradient buffer laid out in REVERSE parameter order = the order gradients become ready
-        order = list(reversed(self.params))
-        offs, total = [], 0
-        for p in order:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
-        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        super().__init__(module)
+        dev = self.flat.device
         cap = max(1, int(bucket_mb * (1 << 20) / self.flat.element_size()))
+        total = self.flat.numel()
         self.buckets = []                               # [start, end, n_params]
         self._bucket_of = {}
         start, count = 0, 0
-        for p, o in zip(order, offs):
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        for p, o in zip(self.order, self.offs):
             self._bucket_of[p] = len(self.buckets)
             count += 1
             end = o + (p.numel() + 3) // 4 * 4
@@ -67,10 +81,6 @@ class GradientAllReducer:
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
 
     # ------------------------------------------------------------------------------------------------
-    def zero_grad(self) -> None:
-        """Gradients stay views of the flat buffer: zero it in one pass (instead of optimizer.zero_grad())."""
-        self.flat.zero_()
-
     def arm(self, last_micro_step: bool = True) -> None:
         """Call before every backward: buckets are reduced during that backward only when it is the last micro-step."""
         self._armed = bool(last_micro_step)
