@@ -107,7 +107,10 @@ __device__ __forceinline__ void stage_taps(const DgradParams& P, int c, float* w
     }
 }
 
-template <int T, int CB, bool TMA>
+// GEN = false: the Block data gradient (natural family always present, no bias) -- the instantiation the training step
+// runs, kept free of the general modes' branches (they cost registers: the T = 32 epilogue spilled with them);
+// GEN = true: single-family modes (K x 5 alone) and the per-channel bias of the merged inference layer.
+template <int T, int CB, bool TMA, bool GEN>
 __global__ void __launch_bounds__(dg::threads(T), 1)
 lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap nmap, DgradParams P) {
   using namespace dg;
@@ -137,7 +140,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   const int c_first = n_units > 0 ? (int)(g0 / upc) : 0;
   const int c_last = n_units > 0 ? (int)((g1 - 1) / upc) : -1;
   const int KL = P.KL, KN = P.KN, H = P.H, W = P.W;
-  const bool has_t = P.has_t != 0, has_n = P.has_n != 0;
+  const bool has_t = P.has_t != 0, has_n = GEN ? (P.has_n != 0) : true;
 
   constexpr int B_N_FULL = 0, B_N_EMPTY = kNStages, B_S_FULL = 2 * kNStages, B_S_EMPTY = B_S_FULL + kSStages,
                 B_T_FULL = B_S_EMPTY + kSStages, B_T_EMPTY = B_T_FULL + 1, B_ACC_FULL = B_T_EMPTY + 1,
@@ -430,7 +433,7 @@ lk_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + ab));
         }
-        if (P.bias) {
+        if (GEN && P.bias) {
           const float bv = __ldg(P.bias + c);
 #pragma unroll
           for (int k = 0; k < T; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + bv);
@@ -495,9 +498,15 @@ static int launch_dgrad(const CUtensorMap& mt, const CUtensorMap& mn, DgradParam
   P.units_per_c = plan.units_per_c;
   P.per_cta = plan.per_cta;
   P.splits = plan.splits;
-  auto kern = lk_dgrad_tc_kernel<T, CB, TMA>;
-  SLAK_SET_MAX_SMEM(kern, Cf::kSmem);
-  kern<<<plan.grid, dg::threads(T), Cf::kSmem, st>>>(mt, mn, P);
+  if (P.has_n && !P.bias) {
+    auto kern = lk_dgrad_tc_kernel<T, CB, TMA, false>;
+    SLAK_SET_MAX_SMEM(kern, Cf::kSmem);
+    kern<<<plan.grid, dg::threads(T), Cf::kSmem, st>>>(mt, mn, P);
+  } else {
+    auto kern = lk_dgrad_tc_kernel<T, CB, TMA, true>;
+    SLAK_SET_MAX_SMEM(kern, Cf::kSmem);
+    kern<<<plan.grid, dg::threads(T), Cf::kSmem, st>>>(mt, mn, P);
+  }
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }

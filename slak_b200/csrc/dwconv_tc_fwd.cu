@@ -450,10 +450,18 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
           if (want_stats && ok) {
             // columns >= W of the accumulator are exact zeros (zero Toeplitz rows): no per-element predicate, and
             // four independent chains instead of one 32-long dependent one
-            float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+            // packed fp32 (FADD2 / FFMA2): two columns per instruction, four independent chains
+            f2 s2[2] = {splat(0.f), splat(0.f)}, q2[2] = {splat(0.f), splat(0.f)};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const float f = __uint_as_float(w[j]); s[j & 3] += f; q[j & 3] = fmaf(f, f, q[j & 3]); }
-            st_s[1 + br] += (s[0] + s[1]) + (s[2] + s[3]); st_q[1 + br] += (q[0] + q[1]) + (q[2] + q[3]);
+            for (int j = 0; j < 16; ++j) {
+              const f2 pr = mk2u(w[2 * j], w[2 * j + 1]);
+              s2[j & 1] = add2(s2[j & 1], pr);
+              q2[j & 1] = fma2(pr, pr, q2[j & 1]);
+            }
+            float sa, sb, qa, qb;
+            un2(add2(s2[0], s2[1]), sa, sb);
+            un2(add2(q2[0], q2[1]), qa, qb);
+            st_s[1 + br] += sa + sb; st_q[1 + br] += qa + qb;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -465,10 +473,17 @@ lk3_fwd_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         };
         auto chunk_t = [&](int h, const uint32_t* w) {                // y1^T: column q = row, p = 32h .. 32h+31
           if (want_stats && n < P.N && row < W) {       // rows p >= H of y1 are exact zeros as well
-            float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+            f2 s2[2] = {splat(0.f), splat(0.f)}, q2[2] = {splat(0.f), splat(0.f)};
 #pragma unroll
-            for (int p = 0; p < 32; ++p) { const float f = __uint_as_float(w[p]); s[p & 3] += f; q[p & 3] = fmaf(f, f, q[p & 3]); }
-            st_s[0] += (s[0] + s[1]) + (s[2] + s[3]); st_q[0] += (q[0] + q[1]) + (q[2] + q[3]);
+            for (int p = 0; p < 16; ++p) {
+              const f2 pr = mk2u(w[2 * p], w[2 * p + 1]);
+              s2[p & 1] = add2(s2[p & 1], pr);
+              q2[p & 1] = fma2(pr, pr, q2[p & 1]);
+            }
+            float sa, sb, qa, qb;
+            un2(add2(s2[0], s2[1]), sa, sb);
+            un2(add2(q2[0], q2[1]), qa, qb);
+            st_s[0] += sa + sb; st_q[0] += qa + qb;
           }
 #pragma unroll
           for (int p = 0; p < 32; ++p) {

@@ -364,6 +364,21 @@ __device__ __forceinline__ void load_plane_blocks_cb2(const PieceMap<2>& pm, con
       }
 }
 
+// ---- packed fp32 pairs: FFMA2 / FMUL2 / FADD2, two fp32 lanes per instruction on sm_100a -----------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 mk2u(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void un2(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 splat(float c) { return mk2(c, c); }
+// (lo, hi) -> bf16x2 bits (round to nearest even), and back (exact)
+__device__ __forceinline__ uint32_t pack2(f2 a) { float lo, hi; un2(a, lo, hi); return pack_bf16(lo, hi); }
+__device__ __forceinline__ f2 unpack2(uint32_t b) { return mk2u(b << 16, b & 0xffff0000u); }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+
 template <int NC>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
   if constexpr (NC == 64) { tmem_ld32(taddr, v); tmem_ld32(taddr + 32, v + 32); }

@@ -5,14 +5,14 @@
 #   <tag>_sass_<kernel>.csv.gz  SASS page with stall samples for the kernels named below (first launch of each)
 # usage: tools/ncu_capture.sh <tag>
 set -u
-TAG=${1:-r01_block}
+TAG=${1:-r02_block}
 OUT=gpurun_out
 REP=/tmp/$TAG.ncu-rep
 timeout 800 ncu --set full --import-source on --clock-control none --profile-from-start off \
-  -k regex:"^(lk|bn3|residual|gelu_bwd|wgrad3)" -f -o /tmp/$TAG python tools/ncu_block.py 2 > $OUT/${TAG}_ncu.log 2>&1
+  -k regex:"^(lk|bn3|residual|gelu_bwd|wgrad3|mlp_gemm|colsum|cast_transpose)" -f -o /tmp/$TAG python tools/ncu_block.py 2 > $OUT/${TAG}_ncu.log 2>&1
 tail -2 $OUT/${TAG}_ncu.log
 ncu -i $REP --page raw --csv 2>/dev/null | gzip -9 > $OUT/${TAG}_raw.csv.gz
-for K in lk3_fwd_tc_kernel lk_dgrad_tc_kernel lk3_wgrad_tc_kernel bn3_sum_ln_bwd_kernel gelu_bwd_bias_kernel bn3_sum_ln_fwd_kernel; do
+for K in lk3_fwd_tc_kernel lk_dgrad_tc_kernel lk3_wgrad_tc_kernel bn3_sum_ln_bwd_kernel bn3_sum_ln_fwd_kernel mlp_gemm_nt_kernel mlp_gemm_tn_splitk_kernel; do
   # launches of one kernel are ordered by stage: 1 = 56x56 (T=64 class), 3 = 14x14 (T=16 class)
   for SKIP in 0 2; do
     S=$SKIP

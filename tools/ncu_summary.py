@@ -56,18 +56,20 @@ def main():
             regs=get(r, "launch__registers_per_thread"),
             occ=get(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             smem=get(r, "launch__shared_mem_per_block_dynamic"),
+            tensor=get(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                       get(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")),
         ))
     if md:
-        print("| # | kernel | grid x block | µs | DRAM rd MB | DRAM wr MB | DRAM GB/s | DRAM % | L2 % | L1 % | SM % | regs | occ % |")
-        print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+        print("| # | kernel | grid x block | µs | DRAM rd MB | DRAM wr MB | DRAM GB/s | DRAM % | L2 % | L1 % | SM % | tensor % | regs | occ % |")
+        print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for i, o in enumerate(out):
         nm = o["name"].split("(")[0][-44:]
         if md:
             print(f"| {i} | `{nm}` | {o['grid']} x {o['block']} | {o['us']:.1f} | {o['rd'] / 1e6:.1f} | {o['wr'] / 1e6:.1f} | "
-                  f"{o['gbs']:.0f} | {o['dram_pct']:.0f} | {o['l2_pct']:.0f} | {o['l1_pct']:.0f} | {o['sm_pct']:.0f} | {o['regs']:.0f} | {o['occ']:.0f} |")
+                  f"{o['gbs']:.0f} | {o['dram_pct']:.0f} | {o['l2_pct']:.0f} | {o['l1_pct']:.0f} | {o['sm_pct']:.0f} | {o['tensor']:.0f} | {o['regs']:.0f} | {o['occ']:.0f} |")
         else:
             print(f"{i:3d} {nm:44s} {o['grid']:>14s}x{o['block']:<14s} {o['us']:8.1f}us rd {o['rd'] / 1e6:7.1f} wr {o['wr'] / 1e6:7.1f} MB "
-                  f"{o['gbs']:6.0f} GB/s dram {o['dram_pct']:4.0f}% l2 {o['l2_pct']:4.0f}% l1 {o['l1_pct']:4.0f}% sm {o['sm_pct']:4.0f}% regs {o['regs']:4.0f} occ {o['occ']:4.0f}%")
+                  f"{o['gbs']:6.0f} GB/s dram {o['dram_pct']:4.0f}% l2 {o['l2_pct']:4.0f}% l1 {o['l1_pct']:4.0f}% sm {o['sm_pct']:4.0f}% tc {o['tensor']:4.0f}% regs {o['regs']:4.0f} occ {o['occ']:4.0f}%")
 
 
 if __name__ == "__main__":
