@@ -11,7 +11,7 @@
 //   p   = p * (1 - lr * wd)
 //   m   = lerp(m, g, 1 - beta1)                      weight < 0.5 form: m + w * (g - m)
 //   v   = v * beta2 + (1 - beta2) * (g * g)
-//   den = sqrt(v) * (1 / sqrt(1 - beta2^t)) + eps    (torch divides by a scalar through its reciprocal)
+//   den = sqrt(v) * float(1 / sqrt(1 - beta2^t)) + eps   (torch divides by a Python scalar through its double reciprocal)
 //   p   = p + (-(lr / (1 - beta1^t))) * (m / den)
 //   p   = p * mask                                    IEEE multiply: a pruned negative weight becomes -0.0
 //   ema = (ema * d + p * (1 - d)) * mask + [ema == 0 and mask != 0] * d * p      (masked tensors)
@@ -41,7 +41,7 @@ adamw_mask_ema_kernel(AdamTables T, int chunk_elems, double beta1, double beta2,
     sc[1] = (float)(1.0 - beta1);
     sc[2] = (float)beta2;
     sc[3] = (float)(1.0 - beta2);
-    sc[4] = __fdiv_rn(1.0f, (float)sqrt(bc2));      // torch divides a tensor by a scalar through a float reciprocal
+    sc[4] = (float)(1.0 / sqrt(bc2));               // torch divides a tensor by a Python scalar through the reciprocal taken in double
     sc[5] = (float)(-(lr / bc1));
   }
   __syncthreads();

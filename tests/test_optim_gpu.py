@@ -85,14 +85,15 @@ def test_fused_step_applies_masks_like_optimizer_step_then_apply_mask_and_ema_li
         for (n, p), (_, q) in zip(net.named_parameters(), rnet.named_parameters()):
             gr = (torch.randn(p.shape, generator=g) * 0.05).to(DEV)
             p.grad, q.grad = gr.clone(), gr.clone()
+        old_masks = {n: m.clone() for n, m in mask.masks.items()}
         mask.step()                                   # fused: AdamW + masks + EMA of the parameters in one launch
         ema.update(net, mask)                         # buffers only
         ropt.step()
         with torch.no_grad():
-            for n, q in rnames.items():
-                if n in mask.masks:
-                    q.data = q.data * mask.masks[n]
-            if mask.steps % 3 == 0:                   # the fused side just pruned + grew and re-applied its masks
+            for n, q in rnames.items():               # Masking.step(): optimizer.step(); apply_mask() with the masks of this step
+                if n in old_masks:
+                    q.data = q.data * old_masks[n]
+            if mask.steps % 3 == 0:                   # ... then prune + grow and apply_mask() with the new masks
                 for n, q in rnames.items():
                     if n in mask.masks:
                         q.data = q.data * mask.masks[n]
