@@ -99,7 +99,11 @@ class FusedBlockFunction(torch.autograd.Function):
         KL = w1.size(2)
         dev = x.device
         bf16 = torch.bfloat16
-        xb = x.to(bf16)
+        # the bf16 copy of the residual stream: handed over by the previous Block's residual kernel when there is one
+        # (its `out_bf16` output), else one cast pass
+        xb = cfg.get("xb")
+        if xb is None or xb.shape != x.shape or xb.dtype != bf16 or not xb.is_contiguous():
+            xb = x.to(bf16)
         y1, y2, y3 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
         scale = torch.empty((3, C), dtype=torch.float32, device=dev)
         shift = torch.empty((C,), dtype=torch.float32, device=dev)
@@ -201,7 +205,8 @@ class FusedBlockFunction(torch.autograd.Function):
                 a = F.gelu(h)
                 h2 = torch.addmm(b2.to(bf16), a, W2b.t())
         out = torch.empty_like(x)
-        _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), None, N, C, HW, st),
+        out_b = torch.empty_like(xb) if cfg.get("emit_bf16") else None      # the next Block's conv input, written in this pass
+        _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), _p(out_b), N, C, HW, st),
             "slak_block_residual_fwd")
         ops._count(2)
         ctx.cfg = cfg
@@ -211,10 +216,13 @@ class FusedBlockFunction(torch.autograd.Function):
         ctx.dims = (N, C, H, W, KL)
         ctx.save_for_backward(xb, w1, w2, w3, bw1, bw2, bw3, y1, y2, y3, scale, shift, mean, istd, lnw, mu, rstd,
                               xn, h, a, h2, W1b, W2b, gamma, dp, W1t, W2t)
+        if out_b is not None:
+            ctx.mark_non_differentiable(out_b)
+            return out, out_b
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, *unused):
         with torch.cuda.device(dout.device):
             return FusedBlockFunction._backward(ctx, dout)
 
@@ -416,8 +424,15 @@ def fused_block_forward(block, x):
     if block.training and p > 0.0:
         keep = 1.0 - p
         dp = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device).bernoulli_(keep).div_(keep)
-    return FusedBlockFunction.apply(
+    cfg["xb"] = getattr(x, "_slak_bf16", None)                 # left there by the previous fused Block
+    cfg["emit_bf16"] = bool(getattr(block, "_slak_emit_bf16", False))
+    res = FusedBlockFunction.apply(
         x, lk.LoRA1.conv.weight, lk.LoRA2.conv.weight, lk.small_conv.conv.weight,
         bns[0].weight, bns[1].weight, bns[2].weight, bns[0].bias, bns[1].bias, bns[2].bias,
         block.norm.weight, block.norm.bias, block.pwconv1.weight, block.pwconv1.bias, block.pwconv2.weight,
         block.pwconv2.bias, block.gamma, dp, cfg)
+    if isinstance(res, tuple):
+        out, out_b = res
+        out._slak_bf16 = out_b
+        return out
+    return res

@@ -123,6 +123,17 @@ class FusedAdamW(torch.optim.Optimizer):
             emas.append(ema_of.get(p))
         return _Tables(ps, gs, ms, vs, masks, emas, dev)
 
+    @torch.no_grad()
+    def remask_ema(self) -> None:
+        """After a prune-and-grow (Masking.truncate_weights) the attached EMA takes the new masks at once, as
+        ModelEma.update(model, mask) -- which the reference runs after mask.step() -- would (model_sema.py:83-88)."""
+        if self._ema is None or self._tables is None:
+            return
+        _, _, _, _, masks, emas = self._tables.keep
+        for m, e in zip(masks or [], emas or []):
+            if m is not None and e is not None:
+                e.mul_(m)
+
     def set_model(self, model) -> None:
         """Names for attach_ema without a Masking: wraps the model in a minimal name provider."""
         class _Names:

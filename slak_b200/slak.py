@@ -324,6 +324,8 @@ class SLaK(nn.Module):
             blocks = [Block(dim=dims[i], drop_path=rates[at + j], layer_scale_init_value=layer_scale_init_value,
                             kernel_size=(kernel_size[i], kernel_size[-1]), Decom=Decom, bn=bn)
                       for j in range(depths[i])]
+            for b_ in blocks[:-1]:
+                b_._slak_emit_bf16 = True      # its successor is a Block: the fused residual kernel also writes the bf16 copy
             self.stages.append(nn.Sequential(*blocks))
             at += depths[i]
 

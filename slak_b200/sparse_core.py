@@ -337,6 +337,8 @@ class Masking(object):
         self._zeros_after_prune = None
         self._sync_masks()
         self.apply_mask()
+        if hasattr(self.optimizer, "remask_ema"):      # slak_b200.optim.FusedAdamW with an EMA folded into its step
+            self.optimizer.remask_ema()
 
     # ------------------------------------------------------------------ utilities
     def get_momentum_for_weight(self, weight):
