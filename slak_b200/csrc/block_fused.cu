@@ -16,6 +16,7 @@
 // runs one warp per pixel with lanes over channels.  Reductions are per-CTA partials combined in a
 // fixed order (deterministic).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace slak {
 namespace blk {
@@ -810,7 +811,9 @@ static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_b
   g.N = N; g.C = C; g.HW = HW;
   // tile of PIX pixels x C channels in fp32; PIX a multiple of 8, about 24 KB (several CTAs per SM: the
   // phases of these kernels are latency-bound, occupancy is what hides it)
-  int pix = (24 * 1024 / 4) / C;
+  static int tile_kb = 0;                 // SLAK_GLUE_TILE_KB: tuning knob for the tile size (default 24 KB)
+  if (tile_kb == 0) { const char* e = getenv("SLAK_GLUE_TILE_KB"); tile_kb = e ? atoi(e) : 24; if (tile_kb < 8 || tile_kb > 128) tile_kb = 24; }
+  int pix = (tile_kb * 1024 / 4) / C;
   pix = pix >= 128 ? 128 : (pix >= 64 ? 64 : (pix >= 32 ? 32 : (pix >= 16 ? 16 : 8)));
   while (pix > 8 && pix / 2 >= HW) pix /= 2;
   // small planes whose rows cannot be vectorised (7 x 7: 98-byte rows): an 8-pixel tile reads 16-byte snippets 98 bytes
