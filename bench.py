@@ -267,6 +267,17 @@ def roofline_table(tagged, peak_gbs, peak_tflops, replays):
             row.update(geometry=f"N{N} C{C} {H}x{W} K{KL}", bound="hbm", algorithmic_bytes=b,
                        achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
                        what=what)
+        elif tag.startswith("glue_"):  # fused elementwise / normalisation passes of the Block: HBM
+            N, C, HW = key
+            per = {"glue_ln_fwd": (8, "bn3_sum_ln_fwd: y1..y3 bf16 in, LayerNorm'd NHWC bf16 out"),
+                   "glue_res_fwd": (12, "residual_fwd: x fp32 + h2 bf16 in, out fp32 (+ bf16 copy) out"),
+                   "glue_res_bwd": (8, "residual_bwd: dout fp32 + h2 bf16 in, dh2 bf16 out"),
+                   "glue_ln_bwd": (10, "bn3_sum_ln_bwd: dxn + y1..y3 bf16 in, du bf16 out"),
+                   "glue_bwd_apply": (14, "bn3_bwd_apply: du + y1..y3 in, dy1..dy3 out (bf16)")}[tag]
+            b = N * C * HW * per[0]
+            row.update(geometry=f"N{N} C{C} HW{HW}", bound="hbm", algorithmic_bytes=b,
+                       achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
+                       what=per[1])
         else:                          # pointwise MLP groups: tensor pipe
             M, Cc = key
             fl = {"mlp_fwd": 2, "mlp_bwd": 4}[tag] * 2 * M * Cc * 4 * Cc

@@ -174,8 +174,9 @@ class FusedBlockFunction(torch.autograd.Function):
         xn = torch.empty((N, H, W, C), dtype=bf16, device=dev)
         mu = torch.empty((N * HW,), dtype=torch.float32, device=dev)
         rstd = torch.empty((N * HW,), dtype=torch.float32, device=dev)
-        _ck(lib.slak_bn3_sum_ln_fwd(_p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(lnb), cfg["ln_eps"],
-                                    _p(xn), _p(mu), _p(rstd), N, C, HW, st), "slak_bn3_sum_ln_fwd")
+        with ops.timed("glue_ln_fwd", (N, C, HW)):
+            _ck(lib.slak_bn3_sum_ln_fwd(_p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(lnb), cfg["ln_eps"],
+                                        _p(xn), _p(mu), _p(rstd), N, C, HW, st), "slak_bn3_sum_ln_fwd")
         # pointwise MLP: bf16 operands, fp32 accumulate
         M = N * HW
         xf = xn.view(M, C)
@@ -206,8 +207,9 @@ class FusedBlockFunction(torch.autograd.Function):
                 h2 = torch.addmm(b2.to(bf16), a, W2b.t())
         out = torch.empty_like(x)
         out_b = torch.empty_like(xb) if cfg.get("emit_bf16") else None      # the next Block's conv input, written in this pass
-        _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), _p(out_b), N, C, HW, st),
-            "slak_block_residual_fwd")
+        with ops.timed("glue_res_fwd", (N, C, HW)):
+            _ck(lib.slak_block_residual_fwd(_p(x), _p(h2), _p(gamma), _p(dp), _p(out), _p(out_b), N, C, HW, st),
+                "slak_block_residual_fwd")
         ops._count(2)
         ctx.cfg = cfg
         ctx.fused_mlp = fused_mlp
@@ -246,8 +248,9 @@ class FusedBlockFunction(torch.autograd.Function):
         parts = lib.slak_block_residual_bwd_parts(N, C, HW)
         dh2 = torch.empty((N * HW, C), dtype=bf16, device=dev)
         dgp = torch.empty((parts, 2, C), dtype=torch.float32, device=dev)
-        _ck(lib.slak_block_residual_bwd(_p(dout), _p(h2), _p(gamma), _p(dp), _p(dh2), _p(dgp), N, C, HW, st),
-            "slak_block_residual_bwd")
+        with ops.timed("glue_res_bwd", (N, C, HW)):
+            _ck(lib.slak_block_residual_bwd(_p(dout), _p(h2), _p(gamma), _p(dp), _p(dh2), _p(dgp), N, C, HW, st),
+                "slak_block_residual_bwd")
         dg2 = _colsum(lib, dgp.view(parts, 2 * C), st).view(2, C)
         dgamma, db2 = dg2[0], dg2[1]
         # ---- MLP backward ---------------------------------------------------------------------------------
@@ -287,8 +290,9 @@ class FusedBlockFunction(torch.autograd.Function):
         parts = lib.slak_bn3_sum_ln_bwd_parts(N, C, HW)
         du = torch.empty_like(xb)
         part = torch.empty((parts, 6, C), dtype=torch.float32, device=dev)
-        _ck(lib.slak_bn3_sum_ln_bwd(_p(dxn), _p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(mu), _p(rstd),
-                                    _p(du), _p(part), N, C, HW, st), "slak_bn3_sum_ln_bwd")
+        with ops.timed("glue_ln_bwd", (N, C, HW)):
+            _ck(lib.slak_bn3_sum_ln_bwd(_p(dxn), _p(y1), _p(y2), _p(y3), _p(scale), _p(shift), _p(lnw), _p(mu), _p(rstd),
+                                        _p(du), _p(part), N, C, HW, st), "slak_bn3_sum_ln_bwd")
         coef = torch.empty((9, C), dtype=torch.float32, device=dev)
         dbnw = torch.empty((3, C), dtype=torch.float32, device=dev)
         dbnb = torch.empty((3, C), dtype=torch.float32, device=dev)
@@ -318,8 +322,9 @@ class FusedBlockFunction(torch.autograd.Function):
             _ck(lib.slak_bn3_finalize_bwd(_p(S), _p(S_local), ctx.count, _p(ctx.count_dev), _ptr3(bw1, bw2, bw3),
                                           _p(mean), _p(istd), C, _p(coef), _p(dbnw), _p(dbnb), st), "slak_bn3_finalize_bwd")
         dy1, dy2, dy3 = torch.empty_like(xb), torch.empty_like(xb), torch.empty_like(xb)
-        _ck(lib.slak_bn3_bwd_apply(_p(du), _p(y1), _p(y2), _p(y3), _p(coef), _p(dy1), _p(dy2), _p(dy3), N, C, HW, st),
-            "slak_bn3_bwd_apply")
+        with ops.timed("glue_bwd_apply", (N, C, HW)):
+            _ck(lib.slak_bn3_bwd_apply(_p(du), _p(y1), _p(y2), _p(y3), _p(coef), _p(dy1), _p(dy2), _p(dy3), N, C, HW, st),
+                "slak_bn3_bwd_apply")
         del du
         ops._count(4)
         # ---- depthwise branches: fused tensor-core dgrad / wgrad ------------------------------------------

@@ -806,7 +806,7 @@ int colsum(const float* part, int rows, int cols, float* out, cudaStream_t st) {
   return SLAK_OK;
 }
 
-static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_bytes, size_t per_pix_extra_bytes = 0) {
+static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_bytes) {
   Geo g{};
   g.N = N; g.C = C; g.HW = HW;
   // tile of PIX pixels x C channels in fp32; PIX a multiple of 8, about 24 KB (several CTAs per SM: the
@@ -816,14 +816,6 @@ static Geo make_geo(int N, int C, int HW, int extra_floats_per_c, size_t* smem_b
   int pix = (tile_kb * 1024 / 4) / C;
   pix = pix >= 128 ? 128 : (pix >= 64 ? 64 : (pix >= 32 ? 32 : (pix >= 16 ? 16 : 8)));
   while (pix > 8 && pix / 2 >= HW) pix /= 2;
-  // small planes whose rows cannot be vectorised (7 x 7: 98-byte rows): an 8-pixel tile reads 16-byte snippets 98 bytes
-  // apart.  Take (a large part of) the whole plane per tile instead: consecutive channels' rows are back to back in
-  // NCHW, so the scalar loads of a warp then cover one contiguous run (fewer, fatter tiles: one CTA per SM)
-  if (HW <= 64 && HW % 4 != 0) {
-    int p = (HW + 7) / 8 * 8;
-    while (p > pix && (size_t)C * (p + 1) * 4 + (size_t)extra_floats_per_c * C * 4 + (size_t)p * per_pix_extra_bytes > 150 * 1024) p -= 8;
-    if (p > pix) pix = p;
-  }
   g.PIX = pix;
   g.pitch = pix + 1;
   g.tiles_per_img = (HW + pix - 1) / pix;
@@ -993,7 +985,7 @@ int residual_bwd(const float* dout, const void* h2, const float* gamma, const fl
 }
 
 static Geo ln_bwd_geo(int N, int C, int HW, size_t* smem) {
-  Geo g = make_geo(N, C, HW, 7, smem, 4 * sizeof(float) + ln_bwd_gpitch(C) * sizeof(__nv_bfloat16));   // u tile + accs [6][C] + lnw [C]
+  Geo g = make_geo(N, C, HW, 7, smem);              // u tile + accs [6][C] + lnw [C]
   *smem += (4 * (size_t)g.PIX + 2 * (size_t)kThreads) * sizeof(float) + (size_t)g.PIX * ln_bwd_gpitch(C) * sizeof(__nv_bfloat16);
   return g;
 }
