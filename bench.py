@@ -278,6 +278,23 @@ def roofline_table(tagged, peak_gbs, peak_tflops, replays):
             row.update(geometry=f"N{N} C{C} HW{HW}", bound="hbm", algorithmic_bytes=b,
                        achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
                        what=per[1])
+        elif tag in ("down_ln_fwd", "down_out_fwd", "down_out_bwd", "down_ln_bwd"):   # downsampling layer, HBM passes
+            N, C, HW = key
+            per = {"down_ln_fwd": (6, "ln2d_patch_fwd: x fp32 in, LayerNorm'd patch rows bf16 out"),
+                   "down_out_fwd": (8, "nhwc_to_nchw: GEMM output bf16 in, fp32 NCHW + bf16 copy out"),
+                   "down_out_bwd": (6, "nchw_to_nhwc: dOut fp32 in, token-major bf16 out (+ bias gradient)"),
+                   "down_ln_bwd": (10, "ln2d_patch_bwd: dA bf16 + x fp32 in, dx fp32 out")}[tag]
+            b = N * C * HW * per[0]
+            row.update(geometry=f"N{N} C{C} HW{HW}", bound="hbm", algorithmic_bytes=b,
+                       achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
+                       what=per[1])
+        elif tag in ("down_gemm_fwd", "down_gemm_bwd"):   # 2 x 2 stride-2 convolution as a GEMM over patch rows
+            M, Co, K = key
+            fl = (1 if tag == "down_gemm_fwd" else 2) * 2 * M * Co * K
+            row.update(geometry=f"M{M} Co{Co} K{K}", bound="tensor", algorithmic_flops=fl,
+                       achieved=round(fl / (us * 1e-6) / 1e12, 1), unit="TFLOP/s",
+                       frac=round(fl / (us * 1e-6) / 1e12 / peak_tflops, 4),
+                       what="downsampling conv as GEMM" if tag == "down_gemm_fwd" else "its data + weight gradient GEMMs")
         else:                          # pointwise MLP groups: tensor pipe
             M, Cc = key
             fl = {"mlp_fwd": 2, "mlp_bwd": 4}[tag] * 2 * M * Cc * 4 * Cc

@@ -210,6 +210,23 @@ SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, 
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Downsampling layer between two stages (models/SLaK.py:283-289: LayerNorm(channels_first) -> Conv2d(k=2, s=2)) as
+ * LayerNorm + GEMM (csrc/block_glue2.cu): the LayerNorm writes its bf16 output as the A operand of the convolution-as-GEMM,
+ * A[(n, h/2, w/2)][((h&1)*2 + (w&1))*C + c]; slak_mlp_gemm_nt / slak_mlp_gemm_tn_splitk do the convolution, its data and
+ * weight gradients; the two layout kernels move between the token-major bf16 side and the fp32 NCHW residual stream.
+ * x, dx: fp32 NCHW [N, C, H, W]; C % 8 == 0, C <= 768, H and W even; part: [parts][2][C] (dlnw, dlnb partials).
+ * nchw_to_nhwc also returns the column sums of its bf16 output in part[:, 1, :] ([parts][2][C]): the bias gradient. */
+SLAK_API int slak_ln2d_patch_fwd(const float* x, const float* lnw, const float* lnb, float eps, void* A, float* mean,
+                                 float* rstd, int N, int C, int H, int W, void* stream);
+SLAK_API int slak_ln2d_patch_bwd_parts(int N, int C, int H, int W);
+SLAK_API int slak_ln2d_patch_bwd(const void* dA, const float* x, const float* lnw, const float* mean, const float* rstd,
+                                 float* dx, float* part, int N, int C, int H, int W, void* stream);
+SLAK_API int slak_nhwc_to_nchw(const void* src_bf16, float* dst, void* dst_bf16 /* or NULL */, int N, int C, int HW,
+                               void* stream);
+SLAK_API int slak_nchw_to_nhwc_parts(int N, int C, int HW);
+SLAK_API int slak_nchw_to_nhwc(const float* src, void* dst_bf16, float* part, int N, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Pointwise MLP of a Block on the tensor cores (models/SLaK.py:157-160, pwconv1 -> GELU -> pwconv2, and its backward):
  * tcgen05 GEMMs with the elementwise passes folded into the epilogues (csrc/mlp_tc.cu).  All matrices bf16 row-major,
  * 16-byte aligned, N % 8 == 0, K % 8 == 0, N <= 3072.

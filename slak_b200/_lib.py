@@ -49,6 +49,12 @@ SIGNATURES = {
     "slak_bn3_eval_affine": (_i, [_vp] * 4 + [ctypes.c_float, _i, _vp, _vp, _vp]),
     "slak_bn3_sum_ln_fwd": (_i, [_vp] * 7 + [ctypes.c_float] + [_vp] * 3 + [_i] * 3 + [_vp]),
     "slak_block_residual_fwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
+    "slak_ln2d_patch_fwd": (_i, [_vp] * 3 + [ctypes.c_float] + [_vp] * 3 + [_i] * 4 + [_vp]),
+    "slak_ln2d_patch_bwd_parts": (_i, [_i] * 4),
+    "slak_ln2d_patch_bwd": (_i, [_vp] * 7 + [_i] * 4 + [_vp]),
+    "slak_nhwc_to_nchw": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
+    "slak_nchw_to_nhwc_parts": (_i, [_i] * 3),
+    "slak_nchw_to_nhwc": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
     "slak_block_residual_bwd_parts": (_i, [_i] * 3),
     "slak_block_residual_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
     "slak_gelu_bwd_bias_parts": (_i, [_i64, _i]),

@@ -16,6 +16,7 @@
 // runs one warp per pixel with lanes over channels.  Reductions are per-CTA partials combined in a
 // fixed order (deterministic).
 #include "common.cuh"
+#include "block_glue2.cuh"
 #include <stdlib.h>
 
 namespace slak {
@@ -910,6 +911,10 @@ int bn3_finalize_bwd(const float* S, const float* S_local, double count, const d
 int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, const float* shift,
                    const float* lnw, const float* lnb, float eps, void* xn, float* mu, float* rstd, int N, int C, int HW,
                    cudaStream_t st) {
+  {
+    const int rc = g2::ln_fwd(y1, y2, y3, scale, shift, lnw, lnb, eps, xn, mu, rstd, N, C, HW, st);
+    if (rc != SLAK_G2_UNSUPPORTED) return rc;
+  }
   size_t smem;
   Geo g = make_geo(N, C, HW, 2, &smem);              // u tile + lnw + lnb
   smem += (2 * (size_t)kThreads + 2 * (size_t)g.PIX) * sizeof(float);
@@ -928,6 +933,10 @@ int bn3_sum_ln_fwd(const void* y1, const void* y2, const void* y3, const float* 
 
 int residual_fwd(const float* x, const void* h2, const float* gamma, const float* dp, float* out, void* out_bf16,
                  int N, int C, int HW, cudaStream_t st) {
+  {
+    const int rc = g2::res_fwd(x, h2, gamma, dp, out, out_bf16, N, C, HW, st);
+    if (rc != SLAK_G2_UNSUPPORTED) return rc;
+  }
   size_t smem;
   Geo g = make_geo(N, C, HW, 0, &smem);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
@@ -944,6 +953,7 @@ int residual_fwd(const float* x, const void* h2, const float* gamma, const float
 }
 
 int residual_bwd_parts(int N, int C, int HW) {
+  if (const int p2 = g2::res_bwd_parts(N, C, HW)) return p2;
   size_t smem;
   Geo g = make_geo(N, C, HW, 2 * kWarps, &smem);
   return grid_for(g, smem);
@@ -970,11 +980,15 @@ int gelu_bwd_bias(const void* da, const void* h, void* dh, float* part, long lon
 }
 int residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2, float* dgamma_part,
                  int N, int C, int HW, cudaStream_t st) {
+  {
+    const int rc = g2::res_bwd(dout, h2, gamma, dp, dh2, dgamma_part, N, C, HW, st);
+    if (rc != SLAK_G2_UNSUPPORTED) return rc;
+  }
   size_t smem;
   Geo g = make_geo(N, C, HW, 2 * kWarps, &smem);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
   const int vp = pick_vp(HW, dout, dout, dout, dout);
-  const int grid = grid_for(g, smem);
+  const int grid = residual_bwd_parts(N, C, HW);      // one partial row per CTA: the caller sized the buffer with this
 #define CALL(V)                                                                                                   \
   SLAK_SET_MAX_SMEM(residual_bwd_kernel<V>, smem); \
   residual_bwd_kernel<V><<<grid, kThreads, smem, st>>>(dout, (const __nv_bfloat16*)h2, gamma, dp, (__nv_bfloat16*)dh2, dgamma_part, g)
@@ -990,6 +1004,7 @@ static Geo ln_bwd_geo(int N, int C, int HW, size_t* smem) {
   return g;
 }
 int bn3_sum_ln_bwd_parts(int N, int C, int HW) {
+  if (const int p2 = g2::ln_bwd_parts(N, C, HW)) return p2;
   size_t smem;
   Geo g = ln_bwd_geo(N, C, HW, &smem);
   return grid_for(g, smem);
@@ -997,11 +1012,15 @@ int bn3_sum_ln_bwd_parts(int N, int C, int HW) {
 int bn3_sum_ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, const float* scale,
                    const float* shift, const float* lnw, const float* mu, const float* rstd, void* du, float* part,
                    int N, int C, int HW, cudaStream_t st) {
+  {
+    const int rc = g2::ln_bwd(dxn, y1, y2, y3, scale, shift, lnw, mu, rstd, du, part, N, C, HW, st);
+    if (rc != SLAK_G2_UNSUPPORTED) return rc;
+  }
   size_t smem;
   Geo g = ln_bwd_geo(N, C, HW, &smem);
   SLAK_REQUIRE(smem <= 200 * 1024, SLAK_ERR_UNSUPPORTED, "C=%d too large for the fused Block kernels", C);
   const int vp = pick_vp(HW, y1, y2, y3, du);
-  const int grid = grid_for(g, smem);
+  const int grid = bn3_sum_ln_bwd_parts(N, C, HW);    // one partial row per CTA: the caller sized the buffer with this
 #define CALL(V)                                                                                                   \
   SLAK_SET_MAX_SMEM(bn3_sum_ln_bwd_kernel<V>, smem); \
   bn3_sum_ln_bwd_kernel<V><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)dxn, (const __nv_bfloat16*)y1,       \

@@ -1,5 +1,6 @@
 // extern "C" entry points of libslak_b200.so (see include/slak_b200.h).
 #include "common.cuh"
+#include "block_glue2.cuh"
 #include <stdarg.h>
 #include <string.h>
 
@@ -359,6 +360,27 @@ SLAK_API int slak_block_residual_fwd(const float* x, const void* h2, const float
                                      void* out_bf16, int N, int C, int HW, void* stream) {
   SLAK_REQUIRE(x && h2 && gamma && out && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
   return blk::residual_fwd(x, h2, gamma, dp, out, out_bf16, N, C, HW, (cudaStream_t)stream);
+}
+
+SLAK_API int slak_ln2d_patch_fwd(const float* x, const float* lnw, const float* lnb, float eps, void* A, float* mean,
+                                 float* rstd, int N, int C, int H, int W, void* stream) {
+  SLAK_REQUIRE(x && lnw && lnb && A && mean && rstd && N > 0 && C > 0 && H > 0 && W > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::ln2d_patch_fwd(x, lnw, lnb, eps, A, mean, rstd, N, C, H, W, (cudaStream_t)stream);
+}
+SLAK_API int slak_ln2d_patch_bwd_parts(int N, int C, int H, int W) { return blk::g2::ln2d_patch_bwd_parts(N, C, H, W); }
+SLAK_API int slak_ln2d_patch_bwd(const void* dA, const float* x, const float* lnw, const float* mean, const float* rstd,
+                                 float* dx, float* part, int N, int C, int H, int W, void* stream) {
+  SLAK_REQUIRE(dA && x && lnw && mean && rstd && dx && part && N > 0 && C > 0 && H > 0 && W > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::ln2d_patch_bwd(dA, x, lnw, mean, rstd, dx, part, N, C, H, W, (cudaStream_t)stream);
+}
+SLAK_API int slak_nhwc_to_nchw(const void* src_bf16, float* dst, void* dst_bf16, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(src_bf16 && dst && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::nhwc_to_nchw(src_bf16, dst, dst_bf16, N, C, HW, (cudaStream_t)stream);
+}
+SLAK_API int slak_nchw_to_nhwc_parts(int N, int C, int HW) { return blk::g2::nchw_to_nhwc_parts(N, C, HW); }
+SLAK_API int slak_nchw_to_nhwc(const float* src, void* dst_bf16, float* part, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(src && dst_bf16 && part && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::nchw_to_nhwc(src, dst_bf16, part, N, C, HW, (cudaStream_t)stream);
 }
 
 SLAK_API int slak_block_residual_bwd_parts(int N, int C, int HW) { return blk::residual_bwd_parts(N, C, HW); }

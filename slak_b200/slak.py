@@ -14,16 +14,20 @@ stay stock PyTorch modules (out of scope).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from . import block as block_mod
+from . import downsample as downsample_mod
 from . import ops
 from .dwconv import DepthWiseConv2dImplicitGEMM
 
 use_sync_bn = True
 FUSED_BLOCK = True      # route eligible Blocks through the fused node (slak_b200/block.py)
+FUSED_DOWNSAMPLE = os.environ.get("SLAK_FUSED_DOWNSAMPLE", "1") == "1"   # downsampling layers through slak_b200/downsample.py
 
 
 # ---- small utilities the reference takes from timm (timm is not a dependency here) --------
@@ -342,8 +346,14 @@ class SLaK(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def forward_features(self, x):
-        for down, stage in zip(self.downsample_layers, self.stages):
-            x = stage(down(x))
+        for i, (down, stage) in enumerate(zip(self.downsample_layers, self.stages)):
+            if (i > 0 and FUSED_DOWNSAMPLE and x.is_cuda and torch.is_autocast_enabled()
+                    and downsample_mod.fused_downsample_supported(down[0], down[1], x)):
+                # LayerNorm + 2x2 stride-2 conv as LayerNorm -> patch rows -> tcgen05 GEMM (slak_b200/downsample.py)
+                x = downsample_mod.fused_downsample(down[0], down[1], x)
+            else:
+                x = down(x)
+            x = stage(x)
         return self.norm(x.mean([-2, -1]))
 
     def forward(self, x):
