@@ -288,6 +288,23 @@ def roofline_table(tagged, peak_gbs, peak_tflops, replays):
             row.update(geometry=f"N{N} C{C} HW{HW}", bound="hbm", algorithmic_bytes=b,
                        achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
                        what=per[1])
+        elif tag in ("stem_patch", "stem_ln_fwd", "stem_ln_bwd"):   # stem, HBM passes
+            N, C, HW = key
+            if tag == "stem_patch":
+                b, what = N * C * HW * 4 + N * (HW // 16) * 128, "patchify4: image fp32 in, 64-wide bf16 patch rows out"
+            elif tag == "stem_ln_fwd":
+                b, what = N * C * HW * 8, "ln_rows_fwd: GEMM output bf16 in, LayerNorm'd fp32 NCHW + bf16 copy out"
+            else:
+                b, what = N * C * HW * 8, "ln_rows_bwd: dOut fp32 + GEMM output bf16 in, dY bf16 out"
+            row.update(geometry=f"N{N} C{C} HW{HW}", bound="hbm", algorithmic_bytes=b,
+                       achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
+                       what=what)
+        elif tag in ("stem_gemm_fwd", "stem_gemm_bwd"):             # K = 64: these are HBM passes over A and Y / dY
+            M, Co, K = key
+            b = M * (K + Co) * 2
+            row.update(geometry=f"M{M} Co{Co} K{K}", bound="hbm", algorithmic_bytes=b,
+                       achieved=round(b / (us * 1e-6) / 1e9, 1), unit="GB/s", frac=round(b / (us * 1e-6) / 1e9 / peak_gbs, 4),
+                       what="stem conv as GEMM (K = 64)" if tag == "stem_gemm_fwd" else "its weight gradient (split-K over tokens)")
         elif tag in ("down_gemm_fwd", "down_gemm_bwd"):   # 2 x 2 stride-2 convolution as a GEMM over patch rows
             M, Co, K = key
             fl = (1 if tag == "down_gemm_fwd" else 2) * 2 * M * Co * K

@@ -227,6 +227,19 @@ SLAK_API int slak_nchw_to_nhwc_parts(int N, int C, int HW);
 SLAK_API int slak_nchw_to_nhwc(const float* src, void* dst_bf16, float* part, int N, int C, int HW, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Stem (models/SLaK.py:277-281: Conv2d(Cin, C, k=4, s=4) -> LayerNorm(channels_first)) as patch rows + GEMM + LayerNorm over
+ * token rows (csrc/block_glue2.cu).  slak_patchify4: A[(n,ho,wo)][ci*16 + kh*4 + kw] (bf16, K = 64, zero beyond 16*Cin) from
+ * the fp32 NCHW image, Cin <= 4, H % 4 == W % 4 == 0.  slak_ln_rows_fwd: Y bf16 [N*HW][C] (GEMM output) -> LayerNorm over C
+ * -> fp32 NCHW (+ bf16 copy or NULL), mean / rstd per token.  slak_ln_rows_bwd: NCHW fp32 gradient -> dY bf16 [N*HW][C];
+ * part [parts][3][C] = dlnw, dlnb and the column sums of dY (the convolution's bias gradient). */
+SLAK_API int slak_patchify4(const float* x, void* A, int N, int Cin, int H, int W, void* stream);
+SLAK_API int slak_ln_rows_fwd(const void* Y, const float* lnw, const float* lnb, float eps, float* out, void* out_bf16,
+                              float* mean, float* rstd, int N, int C, int HW, void* stream);
+SLAK_API int slak_ln_rows_bwd_parts(int N, int C, int HW);
+SLAK_API int slak_ln_rows_bwd(const float* dout, const void* Y, const float* lnw, const float* mean, const float* rstd,
+                              void* dY, float* part, int N, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Pointwise MLP of a Block on the tensor cores (models/SLaK.py:157-160, pwconv1 -> GELU -> pwconv2, and its backward):
  * tcgen05 GEMMs with the elementwise passes folded into the epilogues (csrc/mlp_tc.cu).  All matrices bf16 row-major,
  * 16-byte aligned, N % 8 == 0, K % 8 == 0, N <= 3072.

@@ -55,6 +55,10 @@ SIGNATURES = {
     "slak_nhwc_to_nchw": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
     "slak_nchw_to_nhwc_parts": (_i, [_i] * 3),
     "slak_nchw_to_nhwc": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
+    "slak_patchify4": (_i, [_vp] * 2 + [_i] * 4 + [_vp]),
+    "slak_ln_rows_fwd": (_i, [_vp] * 3 + [ctypes.c_float] + [_vp] * 4 + [_i] * 3 + [_vp]),
+    "slak_ln_rows_bwd_parts": (_i, [_i] * 3),
+    "slak_ln_rows_bwd": (_i, [_vp] * 7 + [_i] * 3 + [_vp]),
     "slak_block_residual_bwd_parts": (_i, [_i] * 3),
     "slak_block_residual_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
     "slak_gelu_bwd_bias_parts": (_i, [_i64, _i]),

@@ -897,6 +897,246 @@ ln2d_patch_bwd_kernel(const __nv_bfloat16* __restrict__ dA, const float* __restr
   }
 }
 
+
+// ====================================================================================================================
+// Stem (models/SLaK.py:277-281: Conv2d(3, C, k=4, s=4) -> LayerNorm(channels_first)): patch rows of the image, the
+// convolution as a GEMM (mlp_tc.cu), then LayerNorm over the channels of each token row with the NCHW residual stream
+// (fp32 + bf16 copy) as output.  Backward: LayerNorm backward from the NCHW gradient to token rows (dY, bf16), the
+// weight gradient is the split-K GEMM dY^T A; the image needs no gradient.
+// ====================================================================================================================
+// A[(n, ho, wo)][ci*16 + kh*4 + kw] = x[n, ci, 4*ho + kh, 4*wo + kw] (bf16), columns >= 16*Cin zero up to K = 64.
+// One thread per (token, 4-pixel piece): a warp writes 256 contiguous bytes and reads whole 32-byte sectors.
+__global__ void __launch_bounds__(256) patchify4_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int N, int Cin,
+                                                        int H, int W, size_t total /* tokens * 16 */) {
+  const int Ho = H / 4, Wo = W / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int piece = (int)(i & 15);
+    const size_t token = i >> 4;
+    const int wo = (int)(token % Wo);
+    const size_t nh = token / Wo;
+    const int ho = (int)(nh % Ho), n = (int)(nh / Ho);
+    const int ci = piece >> 2, kh = piece & 3;
+    uint2 o = make_uint2(0u, 0u);
+    if (ci < Cin) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)n * Cin + ci) * H + 4 * ho + kh) * W + 4 * wo);
+      o.x = tc::pack_bf16(v.x, v.y); o.y = tc::pack_bf16(v.z, v.w);
+    }
+    *reinterpret_cast<uint2*>(A + token * 64 + piece * 4) = o;
+  }
+}
+
+template <int LW>
+__global__ void __launch_bounds__(kThreads, 2)
+ln_rows_fwd_kernel(const __nv_bfloat16* __restrict__ Y, const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
+                   float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ mu, float* __restrict__ rstd,
+                   G2 g) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* red = reinterpret_cast<float*>(smem);
+  float* red2 = red + 4096;
+  float* cst = red2 + kThreads;                               // [2][PIX]  r, -mean*r
+  float* lnw_s = cst + 2 * g.PIX;
+  float* lnb_s = lnw_s + g.C;
+  __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(lnb_s + g.C);
+  const int tid = threadIdx.x, C = g.C, HW = g.HW;
+  const int sp = tid & ((1 << g.vshift) - 1), j0 = sp * kSpan;
+  int ci[kItems];
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) ci[i] = (tid + i * kThreads) >> g.vshift;
+  for (int c = tid; c < C; c += kThreads) { lnw_s[c] = lnw[c]; lnb_s[c] = lnb[c]; }
+  const RowWalk rw = row_walk(C);
+  const int tvec = g.PIX * C / 8;
+  uint4 hr[kMaxVec];
+  int t = blockIdx.x;
+  if (t < g.total_tiles) { const TileIdx ti = tile_of(g, t); rows_ldg(Y + ((size_t)ti.n * HW + ti.p0) * C, ti.npix * C / 8, hr); }
+  for (; t < g.total_tiles; t += gridDim.x) {
+    const TileIdx ti = tile_of(g, t);
+    const int nv = ti.npix - j0;
+    __syncthreads();                                         // the previous tile's transposed reads are done
+    rows_sts(gs, g, rw, tvec, hr);
+    __syncthreads();
+    if (t + gridDim.x < g.total_tiles) {
+      const TileIdx tn = tile_of(g, t + gridDim.x);
+      rows_ldg(Y + ((size_t)tn.n * HW + tn.p0) * C, tn.npix * C / 8, hr);
+    }
+    f2 d[kItems][4], s[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s[0][k] = 0ull; s[1][k] = 0ull; }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      if (ci[i] < C) {
+        lds_span_t(gs, g.ge, j0, ci[i], d[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s[0][k] = add2(s[0][k], d[i][k]); s[1][k] = fma2(d[i][k], d[i][k], s[1][k]); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[i][k] = 0ull;
+      }
+    }
+    pix_partials_store<2>(red, g, sp, s);
+    __syncthreads();
+    pix_partials_fold<2>(red, red2, g);
+    __syncthreads();
+    if (tid < g.PIX) {
+      const float m = pix_total<2>(red2, g, 0, tid) * g.invC;
+      const float var = fmaxf(pix_total<2>(red2, g, 1, tid) * g.invC - m * m, 0.f);
+      const float r = rsqrtf(var + eps);
+      cst[tid] = r; cst[g.PIX + tid] = -m * r;
+      if (tid < ti.npix) {
+        const size_t pix = (size_t)ti.n * HW + ti.p0 + tid;
+        mu[pix] = m; rstd[pix] = r;
+      }
+    }
+    __syncthreads();
+    f2 r2[4], nm2[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(cst + j0 + 4 * k);
+      const float4 b = *reinterpret_cast<const float4*>(cst + g.PIX + j0 + 4 * k);
+      r2[2 * k] = mk2(a.x, a.y); r2[2 * k + 1] = mk2(a.z, a.w);
+      nm2[2 * k] = mk2(b.x, b.y); nm2[2 * k + 1] = mk2(b.z, b.w);
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      if (ci[i] < C && nv > 0) {
+        const f2 w2 = splat(lnw_s[ci[i]]), b2 = splat(lnb_s[ci[i]]);
+        f2 o[4];
+        uint32_t ob[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[k] = fma2(fma2(d[i][k], r2[k], nm2[k]), w2, b2); ob[k] = pack2(o[k]); }
+        const size_t off = ((size_t)ti.n * C + ci[i]) * HW + ti.p0 + j0;
+        stg_span_f32<LW>(out + off, nv, o);
+        if (out_bf16) stg_span<LW>(out_bf16 + off, nv, ob);
+      }
+    }
+  }
+}
+
+// part per CTA: [3][C] = dlnw, dlnb, column sums of dY (the convolution's bias gradient)
+template <int LW>
+__global__ void __launch_bounds__(kThreads, 2)
+ln_rows_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ Y, const float* __restrict__ lnw,
+                   const float* __restrict__ mu, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dY,
+                   float* __restrict__ part, G2 g) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* red = reinterpret_cast<float*>(smem);
+  float* red2 = red + 4096;
+  float* cst = red2 + kThreads;                               // [3][PIX] r, alpha, beta
+  float* mus = cst + 3 * g.PIX;
+  float* rs = mus + g.PIX;
+  __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(rs + g.PIX);
+  const int tid = threadIdx.x, C = g.C, HW = g.HW;
+  const int spr = 1 << g.vshift, sp = tid & (spr - 1), j0 = sp * kSpan;
+  int ci[kItems];
+  float wi[kItems], a2[kItems];
+  f2 A0[kItems], A1[kItems];
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    ci[i] = (tid + i * kThreads) >> g.vshift; wi[i] = ci[i] < C ? lnw[ci[i]] : 0.f;
+    A0[i] = 0ull; A1[i] = 0ull; a2[i] = 0.f;
+  }
+  const RowWalk rw = row_walk(C);
+  const int tvec = g.PIX * C / 8;
+  for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+    const TileIdx ti = tile_of(g, t);
+    const int nv = ti.npix - j0;
+    uint4 hr[kMaxVec];
+    f2 gg[kItems][4], d[kItems][4];
+    rows_ldg(Y + ((size_t)ti.n * HW + ti.p0) * C, ti.npix * C / 8, hr);
+#pragma unroll
+    for (int i = 0; i < kItems; ++i)
+      ldg_span_f32<LW>(dout + ((size_t)ti.n * C + ci[i]) * HW + ti.p0 + j0, ci[i] < C ? nv : 0, gg[i]);
+    float mval = 0.f, rval = 0.f;
+    if (tid < ti.npix) { mval = mu[(size_t)ti.n * HW + ti.p0 + tid]; rval = rstd[(size_t)ti.n * HW + ti.p0 + tid]; }
+    __syncthreads();                                         // the previous tile's rows have been copied out
+    rows_sts(gs, g, rw, tvec, hr);
+    if (tid < g.PIX) { mus[tid] = mval; rs[tid] = rval; }
+    __syncthreads();
+    {
+      f2 nm[4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(mus + j0 + 4 * k);
+        nm[2 * k] = mk2(-a.x, -a.y); nm[2 * k + 1] = mk2(-a.z, -a.w);
+      }
+      f2 s[2][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s[0][k] = 0ull; s[1][k] = 0ull; }
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        if (ci[i] < C) {
+          lds_span_t(gs, g.ge, j0, ci[i], d[i]);
+          const f2 w2 = splat(wi[i]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            d[i][k] = add2(d[i][k], nm[k]);
+            const f2 gw = mul2(gg[i][k], w2);
+            s[0][k] = add2(s[0][k], gw);
+            s[1][k] = fma2(gw, d[i][k], s[1][k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d[i][k] = 0ull;
+        }
+      }
+      pix_partials_store<2>(red, g, sp, s);
+    }
+    __syncthreads();
+    pix_partials_fold<2>(red, red2, g);
+    __syncthreads();
+    if (tid < g.PIX) {
+      const float r = rs[tid];
+      const float m1 = pix_total<2>(red2, g, 0, tid) * g.invC;
+      const float m2 = r * pix_total<2>(red2, g, 1, tid) * g.invC;
+      cst[tid] = r; cst[g.PIX + tid] = -r * m1; cst[2 * g.PIX + tid] = -r * r * m2;
+    }
+    __syncthreads();
+    {
+      f2 r2[4], al[4], be[4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(cst + j0 + 4 * k);
+        const float4 b = *reinterpret_cast<const float4*>(cst + g.PIX + j0 + 4 * k);
+        const float4 e = *reinterpret_cast<const float4*>(cst + 2 * g.PIX + j0 + 4 * k);
+        r2[2 * k] = mk2(a.x, a.y); r2[2 * k + 1] = mk2(a.z, a.w);
+        al[2 * k] = mk2(b.x, b.y); al[2 * k + 1] = mk2(b.z, b.w);
+        be[2 * k] = mk2(e.x, e.y); be[2 * k + 1] = mk2(e.z, e.w);
+      }
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        if (ci[i] < C) {                                       // pixels beyond the tile: r = alpha = beta = 0 and g = 0 -> zeros
+          const f2 w2 = splat(wi[i]);
+          uint32_t ob[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ob[k] = pack2(fma2(mul2(r2[k], w2), gg[i][k], fma2(be[k], d[i][k], al[k])));
+            A0[i] = fma2(gg[i][k], mul2(d[i][k], r2[k]), A0[i]);
+            A1[i] = add2(A1[i], gg[i][k]);
+            fh_add(a2[i], ob[k]);
+          }
+          sts_span_t(gs, g.ge, j0, ci[i], ob);                 // in place: this thread owns these 8 elements
+        }
+      }
+    }
+    __syncthreads();
+    rows_out(dY + ((size_t)ti.n * HW + ti.p0) * C, gs, g, rw, ti.npix * C / 8);
+  }
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    float lo, hi;
+    un2(A0[i], lo, hi); float a = lo + hi;
+    un2(A1[i], lo, hi); float b = lo + hi;
+    float c3 = a2[i];
+    for (int o = 1; o < spr; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    if (sp == 0 && ci[i] < C) {
+      part[(size_t)blockIdx.x * 3 * C + ci[i]] = a;
+      part[(size_t)blockIdx.x * 3 * C + C + ci[i]] = b;
+      part[(size_t)blockIdx.x * 3 * C + 2 * C + ci[i]] = c3;
+    }
+  }
+}
+
 // ====================================================================================================================
 // host side
 // ====================================================================================================================
@@ -1076,6 +1316,56 @@ int nchw_to_nhwc(const float* src, void* dst_bf16, float* part, int N, int C, in
   const int rc = res_bwd(src, nullptr, nullptr, nullptr, dst_bf16, part, N, C, HW, st);
   SLAK_REQUIRE(rc != SLAK_G2_UNSUPPORTED, SLAK_ERR_UNSUPPORTED, "nchw_to_nhwc: C=%d must be a multiple of 8 and <= 768", C);
   return rc;
+}
+
+
+// ---- stem -------------------------------------------------------------------------------------------------------------
+int patchify4(const float* x, void* A, int N, int Cin, int H, int W, cudaStream_t st) {
+  SLAK_REQUIRE(Cin >= 1 && Cin <= 4 && H % 4 == 0 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(A) & 15) == 0, SLAK_ERR_UNSUPPORTED,
+               "patchify4: Cin=%d (<= 4), H=%d, W=%d (multiples of 4), 16-byte aligned tensors", Cin, H, W);
+  const size_t total = (size_t)N * (H / 4) * (W / 4) * 16;
+  size_t grid = (total + 255) / 256;
+  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+  patchify4_kernel<<<(int)grid, 256, 0, st>>>(x, (__nv_bfloat16*)A, N, Cin, H, W, total);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+int ln_rows_fwd(const void* Y, const float* lnw, const float* lnb, float eps, float* out, void* out_bf16, float* mu, float* rstd,
+                int N, int C, int HW, cudaStream_t st) {
+  G2 g;
+  SLAK_REQUIRE(make_g2(N, C, HW, &g) && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, SLAK_ERR_UNSUPPORTED,
+               "ln_rows_fwd: C=%d must be a multiple of 8 and <= 768", C);
+  const size_t smem = (4096 + kThreads + 2 * (size_t)g.PIX + 2 * (size_t)C) * sizeof(float) + gs_bytes(g);
+  const int lw = lw_of(HW, (uintptr_t)out_bf16, (uintptr_t)out);
+  const int grid = grid_of(g, 2);
+#define CALL(V)                                                                                                      \
+  SLAK_SET_MAX_SMEM(ln_rows_fwd_kernel<V>, smem);                                                                   \
+  ln_rows_fwd_kernel<V><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)Y, lnw, lnb, eps, out, (__nv_bfloat16*)out_bf16, mu, rstd, g)
+  SLAK_LW_DISPATCH(lw, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+int ln_rows_bwd_parts(int N, int C, int HW) {
+  G2 g;
+  return make_g2(N, C, HW, &g) ? grid_of(g, 2) : 0;
+}
+int ln_rows_bwd(const float* dout, const void* Y, const float* lnw, const float* mu, const float* rstd, void* dY, float* part,
+                int N, int C, int HW, cudaStream_t st) {
+  G2 g;
+  SLAK_REQUIRE(make_g2(N, C, HW, &g) && ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY)) & 15) == 0,
+               SLAK_ERR_UNSUPPORTED, "ln_rows_bwd: C=%d must be a multiple of 8 and <= 768", C);
+  const size_t smem = (4096 + kThreads + 5 * (size_t)g.PIX) * sizeof(float) + gs_bytes(g);
+  const int lw = lw_of(HW, 0, (uintptr_t)dout);
+  const int grid = grid_of(g, 2);
+#define CALL(V)                                                                                                      \
+  SLAK_SET_MAX_SMEM(ln_rows_bwd_kernel<V>, smem);                                                                   \
+  ln_rows_bwd_kernel<V><<<grid, kThreads, smem, st>>>(dout, (const __nv_bfloat16*)Y, lnw, mu, rstd, (__nv_bfloat16*)dY, part, g)
+  SLAK_LW_DISPATCH(lw, CALL);
+#undef CALL
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
 }
 
 }  // namespace g2

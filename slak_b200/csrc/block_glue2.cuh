@@ -29,6 +29,13 @@ int ln2d_patch_bwd(const void* dA, const float* x, const float* lnw, const float
 int nhwc_to_nchw(const void* h, float* out, void* out_bf16, int N, int C, int HW, cudaStream_t st);
 int nchw_to_nhwc_parts(int N, int C, int HW);
 int nchw_to_nhwc(const float* src, void* dst_bf16, float* part, int N, int C, int HW, cudaStream_t st);
+// stem (4 x 4 stride-4 convolution as a GEMM over patch rows, then LayerNorm over the channels of each token row)
+int patchify4(const float* x, void* A, int N, int Cin, int H, int W, cudaStream_t st);
+int ln_rows_fwd(const void* Y, const float* lnw, const float* lnb, float eps, float* out, void* out_bf16, float* mu, float* rstd,
+                int N, int C, int HW, cudaStream_t st);
+int ln_rows_bwd_parts(int N, int C, int HW);
+int ln_rows_bwd(const float* dout, const void* Y, const float* lnw, const float* mu, const float* rstd, void* dY, float* part,
+                int N, int C, int HW, cudaStream_t st);
 }  // namespace g2
 }  // namespace blk
 }  // namespace slak

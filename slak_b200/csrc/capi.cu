@@ -383,6 +383,22 @@ SLAK_API int slak_nchw_to_nhwc(const float* src, void* dst_bf16, float* part, in
   return blk::g2::nchw_to_nhwc(src, dst_bf16, part, N, C, HW, (cudaStream_t)stream);
 }
 
+SLAK_API int slak_patchify4(const float* x, void* A, int N, int Cin, int H, int W, void* stream) {
+  SLAK_REQUIRE(x && A && N > 0 && Cin > 0 && H > 0 && W > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::patchify4(x, A, N, Cin, H, W, (cudaStream_t)stream);
+}
+SLAK_API int slak_ln_rows_fwd(const void* Y, const float* lnw, const float* lnb, float eps, float* out, void* out_bf16,
+                              float* mean, float* rstd, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(Y && lnw && lnb && out && mean && rstd && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::ln_rows_fwd(Y, lnw, lnb, eps, out, out_bf16, mean, rstd, N, C, HW, (cudaStream_t)stream);
+}
+SLAK_API int slak_ln_rows_bwd_parts(int N, int C, int HW) { return blk::g2::ln_rows_bwd_parts(N, C, HW); }
+SLAK_API int slak_ln_rows_bwd(const float* dout, const void* Y, const float* lnw, const float* mean, const float* rstd,
+                              void* dY, float* part, int N, int C, int HW, void* stream) {
+  SLAK_REQUIRE(dout && Y && lnw && mean && rstd && dY && part && N > 0 && C > 0 && HW > 0, SLAK_ERR_BAD_ARG, "bad argument");
+  return blk::g2::ln_rows_bwd(dout, Y, lnw, mean, rstd, dY, part, N, C, HW, (cudaStream_t)stream);
+}
+
 SLAK_API int slak_block_residual_bwd_parts(int N, int C, int HW) { return blk::residual_bwd_parts(N, C, HW); }
 
 SLAK_API int slak_block_residual_bwd(const float* dout, const void* h2, const float* gamma, const float* dp, void* dh2,

@@ -114,3 +114,96 @@ def fused_downsample(ln, conv, x):
     out, out_b = DownsampleFunction.apply(x, ln.weight, ln.bias, conv.weight, conv.bias, ln.eps)
     out._slak_bf16 = out_b
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Stem: Conv2d(Cin, C, kernel_size=4, stride=4) -> LayerNorm(channels_first)   (reference models/SLaK.py:277-281)
+# ------------------------------------------------------------------------------------------------------------------------
+STEM_K = 64        # patch row length: 16 * Cin (<= 64) values, zero padded (one 128-byte swizzle atom of the GEMM's K loop)
+
+
+def fused_stem_supported(conv, ln, x) -> bool:
+    if not (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous()) or x.requires_grad:
+        return False
+    if not (torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16):
+        return False
+    N, Cin, H, W = x.shape
+    if tuple(conv.kernel_size) != (4, 4) or tuple(conv.stride) != (4, 4) or tuple(conv.padding) != (0, 0):
+        return False
+    if tuple(conv.dilation) != (1, 1) or conv.groups != 1 or conv.bias is None or conv.in_channels != Cin or Cin > 4:
+        return False
+    C = conv.out_channels
+    if C % 8 or C > 768 or H % 4 or W % 4:
+        return False
+    return getattr(ln, "data_format", None) == "channels_first" and ln.weight.dtype == torch.float32 and conv.weight.dtype == torch.float32
+
+
+class StemFunction(torch.autograd.Function):
+    """patch rows of the image -> tcgen05 GEMM + bias -> LayerNorm over token rows -> NCHW fp32 (+ bf16 copy).  The image gets no
+    gradient (fused_stem_supported refuses inputs that require one)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lnw, lnb, eps):
+        lib = _lib.load()
+        N, Cin, H, W = x.shape
+        C = weight.shape[0]
+        Ho, Wo = H // 4, W // 4
+        M = N * Ho * Wo
+        dev, bf16 = x.device, torch.bfloat16
+        with torch.cuda.device(dev):
+            st = _lib.current_stream_ptr()
+            A = torch.empty((M, STEM_K), dtype=bf16, device=dev)
+            with ops.timed("stem_patch", (N, Cin, H * W)):
+                _ck(lib.slak_patchify4(_p(x), _p(A), N, Cin, H, W, st), "slak_patchify4")
+            ops._count(1)
+            Wp = torch.zeros((C, STEM_K), dtype=bf16, device=dev)
+            Wp[:, :Cin * 16] = weight.detach().reshape(C, Cin * 16)
+            Y = torch.empty((M, C), dtype=bf16, device=dev)
+            with ops.timed("stem_gemm_fwd", (M, C, STEM_K)):
+                _gemm_nt(lib, st, EPI_BIAS, A, Wp, bias.detach().float().contiguous(), None, Y, None, None, M, C, STEM_K)
+            out = torch.empty((N, C, Ho, Wo), dtype=torch.float32, device=dev)
+            out_b = torch.empty((N, C, Ho, Wo), dtype=bf16, device=dev)
+            mean = torch.empty(M, dtype=torch.float32, device=dev)
+            rstd = torch.empty_like(mean)
+            with ops.timed("stem_ln_fwd", (N, C, Ho * Wo)):
+                _ck(lib.slak_ln_rows_fwd(_p(Y), _p(lnw), _p(lnb), float(eps), _p(out), _p(out_b), _p(mean), _p(rstd), N, C, Ho * Wo, st),
+                    "slak_ln_rows_fwd")
+            ops._count(1)
+        ctx.save_for_backward(A, Y, lnw, mean, rstd)
+        ctx.dims = (N, Cin, H, W, C)
+        ctx.param_dtypes = (weight.dtype, bias.dtype, lnw.dtype, lnb.dtype)
+        ctx.mark_non_differentiable(out_b)
+        return out, out_b
+
+    @staticmethod
+    def backward(ctx, dout, _unused):
+        lib = _lib.load()
+        A, Y, lnw, mean, rstd = ctx.saved_tensors
+        N, Cin, H, W, C = ctx.dims
+        Ho, Wo = H // 4, W // 4
+        M = N * Ho * Wo
+        dev, bf16 = A.device, torch.bfloat16
+        dout = dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        with torch.cuda.device(dev):
+            st = _lib.current_stream_ptr()
+            parts = lib.slak_ln_rows_bwd_parts(N, C, Ho * Wo)
+            dY = torch.empty((M, C), dtype=bf16, device=dev)
+            part = torch.empty((parts, 3, C), dtype=torch.float32, device=dev)
+            with ops.timed("stem_ln_bwd", (N, C, Ho * Wo)):
+                _ck(lib.slak_ln_rows_bwd(_p(dout), _p(Y), _p(lnw), _p(mean), _p(rstd), _p(dY), _p(part), N, C, Ho * Wo, st),
+                    "slak_ln_rows_bwd")
+            ops._count(1)
+            red = _colsum(lib, part.view(parts, 3 * C), st).view(3, C)
+            with ops.timed("stem_gemm_bwd", (M, C, STEM_K)):
+                dWp = _wgrad(lib, st, dY, A, M, C, STEM_K)             # [C, 64] fp32
+            dW = dWp[:, :Cin * 16].reshape(C, Cin, 4, 4)
+        pd = ctx.param_dtypes
+        return None, dW.to(pd[0]), red[2].to(pd[1]), red[0].to(pd[2]), red[1].to(pd[3]), None
+
+
+def fused_stem(conv, ln, x):
+    out, out_b = StemFunction.apply(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps)
+    out._slak_bf16 = out_b
+    return out

@@ -351,6 +351,10 @@ class SLaK(nn.Module):
                     and downsample_mod.fused_downsample_supported(down[0], down[1], x)):
                 # LayerNorm + 2x2 stride-2 conv as LayerNorm -> patch rows -> tcgen05 GEMM (slak_b200/downsample.py)
                 x = downsample_mod.fused_downsample(down[0], down[1], x)
+            elif (i == 0 and FUSED_DOWNSAMPLE and x.is_cuda and torch.is_autocast_enabled()
+                    and downsample_mod.fused_stem_supported(down[0], down[1], x)):
+                # 4x4 stride-4 conv + LayerNorm as patch rows -> tcgen05 GEMM -> LayerNorm over token rows
+                x = downsample_mod.fused_stem(down[0], down[1], x)
             else:
                 x = down(x)
             x = stage(x)

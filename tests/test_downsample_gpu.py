@@ -74,3 +74,37 @@ def test_slak_model_uses_fused_downsample():
     assert _rel(outs[True][0], outs[False][0]) < 3e-2
     assert _rel(outs[True][1], outs[False][1]) < 5e-2
     assert _rel(outs[True][2], outs[False][2]) < 5e-2
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 16, 16), (3, 24, 8, 24), (2, 96, 224, 224)])
+def test_fused_stem_matches_fp64(N, C, H, W):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from slak_b200 import downsample
+    from slak_b200.slak import LayerNorm
+    torch.manual_seed(C + H)
+    dev = torch.device("cuda:0")
+    conv = nn.Conv2d(3, C, kernel_size=4, stride=4).to(dev)
+    ln = LayerNorm(C, eps=1e-6, data_format="channels_first").to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(C) * 0.2 + 1); ln.bias.copy_(torch.randn(C) * 0.1)
+        conv.weight.copy_(torch.randn_like(conv.weight) * 0.2); conv.bias.copy_(torch.randn(C) * 0.1)
+    x = torch.randn(N, 3, H, W, device=dev)
+    gout = torch.randn(N, C, H // 4, W // 4, device=dev)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert downsample.fused_stem_supported(conv, ln, x)
+        out = downsample.fused_stem(conv, ln, x)
+    out.backward(gout)
+    got = [out.detach(), conv.weight.grad, conv.bias.grad, ln.weight.grad, ln.bias.grad]
+    cw, cb = conv.weight.detach().double().requires_grad_(True), conv.bias.detach().double().requires_grad_(True)
+    w, b = ln.weight.detach().double().requires_grad_(True), ln.bias.detach().double().requires_grad_(True)
+    y = F.conv2d(x.double(), cw, cb, stride=4)
+    u = y.mean(1, keepdim=True)
+    s = (y - u).pow(2).mean(1, keepdim=True)
+    ref = w[:, None, None] * ((y - u) / torch.sqrt(s + 1e-6)) + b[:, None, None]
+    ref.backward(gout.double())
+    want = [ref.detach(), cw.grad, cb.grad, w.grad, b.grad]
+    # the convolution output is rounded to bf16 before the LayerNorm (as under the reference's autocast): 2^-9 on y, amplified
+    # by 1/std in the normalised output where a token's channels are close together
+    for n, g, r, bd in zip(["out", "dW", "db", "dlnw", "dlnb"], got, want, [1.2e-2, 2e-2, 2e-2, 1.5e-2, 4e-3]):
+        assert _rel(g, r) < bd, f"{n}: rel L2 {_rel(g, r):.3e} (bound {bd})"
