@@ -420,11 +420,9 @@ def run_ours(args):
                 loss = F.cross_entropy(out.float(), y_dev[k * B:(k + 1) * B])
                 if UF > 1:
                     loss = loss / UF
-            if dp is not None:
-                dp.arm(last_micro_step=(k == UF - 1))
+            flat.arm(last_micro_step=(k == UF - 1))
             loss.backward()
-        if dp is not None:
-            dp.finish()
+        flat.finish()                                    # gradients gathered into the flat buffer (and all-reduced at N > 1)
         opt.step()
         if mask is not None and not getattr(opt, "fused_mask", False):
             mask.apply_mask()                            # Masking.step() = optimizer.step(); apply_mask(); advance()
