@@ -36,6 +36,11 @@ int mlp_gemm_nt(int epi, const void* a, const void* b, const float* bias, const 
                 float* colpart, int M, int N, int K, cudaStream_t st);
 int mlp_wgrad_splits(int M, int Ma, int Nb);
 int mlp_gemm_tn_splitk(const void* p, const void* q, float* part, int M, int Ma, int Nb, cudaStream_t st);
+namespace dense {
+bool supported(int N, int C, int H, int W, int KL);
+int dgrad(const void* dy1, const void* dy2, const void* dy3, const float* w1, const float* w2, const float* w3, const float* addend,
+          float* dx, int N, int C, int H, int W, int KL, cudaStream_t st);
+}
 size_t lk3_wgrad_tc_workspace(int N, int C, int H, int W, int KL);
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st);
@@ -253,6 +258,8 @@ SLAK_API int slak_lk_branches_bwd_data_f32(const void* dy1, const void* dy2, con
   SLAK_REQUIRE(slak_lk_branches_bwd_uses_tc(N, C, H, W, KL, KS, SLAK_BF16), SLAK_ERR_UNSUPPORTED,
                "fused bwd_data covers only the tensor-core shapes (see slak_lk_branches_uses_tc)");
   cudaStream_t st = (cudaStream_t)stream;
+  if (KS == 5 && addend && tc::dense::supported(N, C, H, W, KL))      // small planes: one dense-GEMM launch for the three branches
+    return tc::dense::dgrad(dy1, dy2, dy3, w1, w2, w3, addend, dx, N, C, H, W, KL, st);
   rc = tc::lk_conv_tc(nullptr, nullptr, dy3, w3, nullptr, tmp, nullptr, nullptr, N, C, H, W, KL, KS, /*flip=*/1, st);
   if (rc) return rc;
   return tc::lk_conv_tc(dy1, w1, dy2, w2, tmp, nullptr, addend, dx, N, C, H, W, KL, KL, /*flip=*/1, st);

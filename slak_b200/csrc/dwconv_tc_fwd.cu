@@ -713,7 +713,16 @@ static int launch_fwd(const CUtensorMap& map, const CUtensorMap* ymaps, FwdParam
   return SLAK_OK;
 }
 
+// dwconv_tc_dense.cu: planes of up to 208 pixels as dense per-channel GEMMs
+namespace dense {
+bool supported(int N, int C, int H, int W, int KL);
+int stats_slots(int N);
+int fwd(const void* x, const float* w1, const float* w2, const float* w3, void* y1, void* y2, void* y3, int N, int C, int H, int W,
+        int KL, float* stats, cudaStream_t st);
+}
+
 int lk3_fwd_tc_splits(int N, int C, int H, int W) {
+  if (dense::supported(N, C, H, W, 5)) return dense::stats_slots(N);
   const TcShape s = tc_shape(H, W);
   if (s.tile == 0) return 0;
   return tc_plan(N, C, s.tile, (128 / s.tile) * (64 / s.tile)).splits * kEpiGroups;   // statistics slots per channel
@@ -724,6 +733,7 @@ int lk3_fwd_tc(const void* x, const float* w1, const float* w2, const float* w3,
   SLAK_REQUIRE(lk3_tc_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   SLAK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SLAK_ERR_BAD_ARG, "x must be 16-byte aligned");
   SLAK_REQUIRE((2 * KL * 5 + 25) * 4 <= 4096, SLAK_ERR_UNSUPPORTED, "kernel side %d too large", KL);
+  if (dense::supported(N, C, H, W, KL)) return dense::fwd(x, w1, w2, w3, y1, y2, y3, N, C, H, W, KL, stats, st);
   const TcShape s = tc_shape(H, W);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
