@@ -12,10 +12,12 @@
 // P x P matrix of the branch, built in shared memory from the channel's taps (a few thousand cycles, hidden behind the
 // previous branch's epilogue).  The dense matrix wastes 3 - 4 x the FLOPs of the separable form, which is irrelevant:
 // 39 MMAs of 128 x 208 x 16 per channel are ~4 k cycles against ~3 k cycles of HBM time for the channel's planes.
-// A plane of P bf16 is only 8- (P = 196) or 2-byte (P = 49) aligned: the tensor maps see G planes as one row of G P
-// elements (a multiple of 16 bytes) and address a plane by its element offset inside the row -- TMA tile coordinates
-// need no alignment (tools/probes/tma_unaligned_probe.cu).  What a 16-byte-granular box cannot store (the last P % 8
-// pixels of a plane) is written by the epilogue threads.
+// A plane of P bf16 is only 8- (P = 196) or 2-byte (P = 49) aligned and TMA boxes must start on 16 bytes in the inner
+// dimension (tools/probes/tma_unaligned_probe.cu: illegal instruction otherwise).  The tensor maps therefore see G planes as
+// one row of G P elements (a multiple of 16 bytes); a plane is loaded from the 16-byte boundary below its first pixel and
+// the matrix is built with its K index shifted by those delta <= 7 elements (the strangers in front meet zero rows).
+// Results leave through a shared-memory slab and coalesced 8- or 2-byte stores (bf16), or TMA boxes where rows are
+// 16-byte aligned (the fp32 gradient of 14 x 14 planes).
 //
 // One CTA = 512 threads: w0 TMA producer + MMA issuer (one thread) | w1 TMEM allocator | w4-7 epilogue (thread = image row =
 // TMEM lane) | w8-15 matrix builders.  Work unit = (channel, tile of 128 images), round-robin over a persistent grid.
@@ -55,6 +57,7 @@ struct Params {
   int G, Gf;                      // planes per tensor-map row: bf16 maps, fp32 maps
   int NK, KB, NPAD;               // k16 steps, 64-pixel K blocks, MMA N (= NK * 16)
   int ntile, units;               // image tiles per channel, work units
+  int dbg;                        // timing experiments (SLAK_DENSE_DBG): 1 = skip the matrix build, 2 = skip the global stores
 };
 
 // barrier indices
@@ -66,66 +69,80 @@ struct Ctx {
   __device__ __forceinline__ uint32_t bar(int i) const { return bar0 + 8u * i; }
 };
 
-// ---- matrix of one branch: Bm[n][k] (K-major SWIZZLE_128B, rows n < NPAD, k < NK*16) ------------------------------------
-// forward: n = output pixel, k = input pixel;  dgrad: n = input pixel, k = output pixel.  Entry = w_b[in - out + pad].
+// ---- matrix of one branch: Bm[n][k] (K-major SWIZZLE_128B, rows n < NPAD, k < kb * 64) ----------------------------------
+// forward: n = output pixel, k - delta = input pixel;  dgrad: n = input pixel, k - delta = output pixel.
+// Entry = w_b[in - out + pad].  The matrix is a band: zero-fill the slabs with 16-byte stores, then write the band only --
+// one item = (row n, image row r of the other side): a run of <= min(kw, W) consecutive k whose taps are consecutive too
+// (ascending for the forward matrix, descending for its transpose).  Taps sit in shared memory as bf16 already.
 template <bool DGRAD>
-__device__ __forceinline__ void build_matrix(const Ctx& cx, const Params& P, int b, int t0, int nthr) {
-  const float* taps = reinterpret_cast<const float*>(cx.sm + kOffTaps);
+__device__ __forceinline__ void build_matrix(const Ctx& cx, const Params& P, int b, int delta, int kbu, int t0, int nthr) {
+  const unsigned short* taps = reinterpret_cast<const unsigned short*>(cx.sm + kOffTaps);
   const uint8_t* hh = cx.sm + kOffHW;
   const uint8_t* ww = hh + 256;
-  const int KL = P.KL;
-  const float* tb = b == 0 ? taps : (b == 1 ? taps + KL * 5 : taps + 2 * KL * 5);
+  const int KL = P.KL, Hh = P.H, Ww = P.W;
+  const unsigned short* tb = b == 0 ? taps : (b == 1 ? taps + KL * 5 : taps + 2 * KL * 5);
   const int kh = b == 0 ? KL : 5, kw = b == 1 ? KL : 5;
   const int ph = kh / 2, pw = kw / 2;
-  const int cpr = P.NK * 2;                               // 16-byte chunks per row
-  const int total = P.NPAD * cpr;
   uint8_t* Bs = cx.sm + kOffB;
-  for (int q = t0; q < total; q += nthr) {
-    const int n = q / cpr, k8 = q - n * cpr;
-    const int kb = k8 >> 3, kc = k8 & 7;
-    uint32_t o[4] = {0u, 0u, 0u, 0u};
-    if (n < P.P) {
-      const int hn = hh[n], wn = ww[n];
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = k8 * 8 + j;
-        float t = 0.f;
-        if (k < P.P) {
-          const int dh = DGRAD ? (hn - (int)hh[k]) : ((int)hh[k] - hn);
-          const int dw = DGRAD ? (wn - (int)ww[k]) : ((int)ww[k] - wn);
-          const int i = dh + ph, jx = dw + pw;
-          if ((unsigned)i < (unsigned)kh && (unsigned)jx < (unsigned)kw) t = tb[i * kw + jx];
-        }
-        v[j] = t;
-      }
-      o[0] = pack_bf16(v[0], v[1]); o[1] = pack_bf16(v[2], v[3]); o[2] = pack_bf16(v[4], v[5]); o[3] = pack_bf16(v[6], v[7]);
-    }
-    *reinterpret_cast<uint4*>(Bs + (size_t)kb * (P.NPAD * 128) + n * 128 + ((kc ^ (n & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+  const int slab = P.NPAD * 128;
+  {
+    const int nvec = kbu * P.NPAD * 8;
+    uint4* z = reinterpret_cast<uint4*>(Bs);
+    for (int i = t0; i < nvec; i += nthr) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  named_bar_sync(2, nthr);
+  const int R = kh < Hh ? kh : Hh;                          // rows of the other side a row n can touch
+  const int items = P.P * R;
+  for (int it = t0; it < items; it += nthr) {
+    const int n = it / R, j = it - n * R;
+    const int hn = hh[n], wn = ww[n];
+    const int r = kh < Hh ? hn - ph + j : j;
+    if ((unsigned)r >= (unsigned)Hh) continue;
+    const int dh = DGRAD ? (hn - r + ph) : (r - hn + ph);
+    if ((unsigned)dh >= (unsigned)kh) continue;
+    const int wlo = max(0, wn - pw), whi = min(Ww - 1, wn + pw);
+    int k = delta + r * Ww + wlo;
+    const unsigned short* tp = tb + dh * kw + (DGRAD ? (wn - wlo + pw) : (wlo - wn + pw));
+    uint8_t* rowp = Bs + n * 128;
+    const int sw = n & 7;
+    for (int w = wlo; w <= whi; ++w, ++k, tp += (DGRAD ? -1 : 1))
+      *reinterpret_cast<unsigned short*>(rowp + (k >> 6) * slab + ((((k >> 3) & 7) ^ sw) << 4) + (k & 7) * 2) = *tp;
   }
 }
 
 __device__ __forceinline__ void load_taps(const Ctx& cx, const Params& P, int c, int t0, int nthr) {
-  float* taps = reinterpret_cast<float*>(cx.sm + kOffTaps);
+  unsigned short* taps = reinterpret_cast<unsigned short*>(cx.sm + kOffTaps);
   const int n1 = P.KL * 5;
   for (int i = t0; i < 2 * n1 + 25; i += nthr) {
     float v;
     if (i < n1) v = P.w[0][(size_t)c * n1 + i];
     else if (i < 2 * n1) v = P.w[1][(size_t)c * n1 + (i - n1)];
     else v = P.w[2][(size_t)c * 25 + (i - 2 * n1)];
-    taps[i] = v;
+    taps[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
 }
 
 // ====================================================================================================================
+// position of channel c's plane inside its tensor-map row: TMA start coordinate (16-byte aligned) and the delta in front
+struct PlanePos { int cg, c0, delta, nk, kb; };
+__device__ __forceinline__ PlanePos plane_pos(const Params& P, int c) {
+  PlanePos pp;
+  pp.cg = c / P.G;
+  const int start = (c - pp.cg * P.G) * P.P;
+  pp.delta = start & 7;
+  pp.c0 = start - pp.delta;
+  pp.nk = (pp.delta + P.P + 15) >> 4;
+  pp.kb = (pp.delta + P.P + 63) >> 6;
+  return pp;
+}
+
 template <bool DGRAD>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CUtensorMap in1, const __grid_constant__ CUtensorMap in2,
-             const __grid_constant__ CUtensorMap of0, const __grid_constant__ CUtensorMap of1, const __grid_constant__ CUtensorMap of2,
-             const __grid_constant__ CUtensorMap op0, const __grid_constant__ CUtensorMap op1, const __grid_constant__ CUtensorMap op2,
-             Params P) {
-  // forward: in0 = x;  of_b / op_b = full (64-pixel, SWIZZLE_128B) and partial (rem8-pixel, unswizzled) store maps of y_b
-  // dgrad  : in_b = dy_b;  of0 / op0 = full (32-pixel fp32) and partial maps of the addend, of1 / op1 of dx
+             const __grid_constant__ CUtensorMap fa_full, const __grid_constant__ CUtensorMap fa_part,
+             const __grid_constant__ CUtensorMap fd_full, const __grid_constant__ CUtensorMap fd_part, Params P) {
+  // forward: in0 = x.   dgrad: in_b = dy_b; fa_* / fd_* = full (32-pixel, SWIZZLE_128B) and partial (rem4-pixel, unswizzled)
+  // fp32 maps of the addend and of dx, used when the fp32 rows are 16-byte aligned (P % 4 == 0)
   extern __shared__ uint8_t smem_raw[];
   Ctx cx;
   const uint32_t raw = smem_u32(smem_raw);
@@ -139,9 +156,10 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
     mbar_init(cx.bar(B_X_FULL), 1); mbar_init(cx.bar(B_X_EMPTY), 1);
     mbar_init(cx.bar(B_B_FULL), 8); mbar_init(cx.bar(B_B_EMPTY), 1);
     for (int a = 0; a < 2; ++a) { mbar_init(cx.bar(B_ACC_FULL + a), 1); mbar_init(cx.bar(B_ACC_EMPTY + a), 4); }
-    for (int s = 0; s < kStgSlabs; ++s) mbar_init(cx.bar(B_H_FULL + s), 1);
+    for (int sl = 0; sl < kStgSlabs; ++sl) mbar_init(cx.bar(B_H_FULL + sl), 1);
     mbar_fence_init();
-    tma_prefetch_desc(&in0); tma_prefetch_desc(&of0); tma_prefetch_desc(&op0);
+    tma_prefetch_desc(&in0);
+    if (DGRAD) { tma_prefetch_desc(&in1); tma_prefetch_desc(&in2); tma_prefetch_desc(&fa_full); tma_prefetch_desc(&fd_full); }
   }
   for (int i = tid; i < 256; i += kThreads) {                     // pixel -> (h, w)
     const int h = i / P.W;
@@ -153,11 +171,6 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int PK = P.KB;
-  const uint32_t xbytes = (uint32_t)PK * kXSlab;
-  const int rem8 = ((P.P & 63) >> 3) << 3;                        // pixels of the partial bf16 store box
-  const int nfull = P.P >> 6;
-  const int tail8 = P.P & 7;
 
   if (warp == 0) {
     // ================= TMA producer + MMA issuer (one thread) =================
@@ -166,16 +179,16 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
       int gc = 0, ld = 0, uit = 0;                                // groups issued, A loads issued, units done
       for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++uit) {
         const int c = u / P.ntile, n0 = (u - c * P.ntile) * 128;
-        const int cg = c / P.G, cin = (c - cg * P.G) * P.P;
+        const PlanePos pp = plane_pos(P, c);
         const int ab = DGRAD ? (uit & 1) : 0;
         for (int g = 0; g < 3; ++g, ++gc) {
           if (DGRAD || g == 0) {                                   // A operand: dy_g (dgrad) / x (forward, once per unit)
             mbar_wait(cx.bar(B_X_EMPTY), (ld & 1) ^ 1);
-            mbar_expect_tx(cx.bar(B_X_FULL), xbytes);
+            mbar_expect_tx(cx.bar(B_X_FULL), (uint32_t)pp.kb * kXSlab);
             const CUtensorMap* m = DGRAD ? (g == 0 ? &in0 : (g == 1 ? &in1 : &in2)) : &in0;
-            for (int kb = 0; kb < PK; ++kb) {
-              tma_load_3d(cx.base + kOffX + kb * kXSlab, m, cx.bar(B_X_FULL), cin + kb * 64, cg, n0);
-              tma_load_3d(cx.base + kOffX + kb * kXSlab + kBox, m, cx.bar(B_X_FULL), cin + kb * 64, cg, n0 + 64);
+            for (int kb = 0; kb < pp.kb; ++kb) {
+              tma_load_3d(cx.base + kOffX + kb * kXSlab, m, cx.bar(B_X_FULL), pp.c0 + kb * 64, pp.cg, n0);
+              tma_load_3d(cx.base + kOffX + kb * kXSlab + kBox, m, cx.bar(B_X_FULL), pp.c0 + kb * 64, pp.cg, n0 + 64);
             }
             mbar_wait(cx.bar(B_X_FULL), ld & 1);
             ++ld;
@@ -191,7 +204,7 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
             acc = tmem + fb * 256;
           }
           tc_fence_after();
-          for (int ks = 0; ks < P.NK; ++ks) {
+          for (int ks = 0; ks < pp.nk; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
             umma_bf16(acc, umma_desc_k_sw128(cx.base + kOffX + kb * kXSlab + kk * 32, 0),
                       umma_desc_k_sw128(cx.base + kOffB + kb * (P.NPAD * 128) + kk * 32, 0), idesc, DGRAD ? ((g | ks) != 0) : (ks != 0));
@@ -213,6 +226,7 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
     int gc = 0;
     for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
       const int c = u / P.ntile;
+      const PlanePos pp = plane_pos(P, c);
       for (int g = 0; g < 3; ++g, ++gc) {
         mbar_wait(cx.bar(B_B_EMPTY), (gc & 1) ^ 1);               // the previous matrix has been consumed
         if (g == 0) {                                             // (its taps as well: they were only read while building)
@@ -220,7 +234,7 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
           load_taps(cx, P, c, t0, 256);
           named_bar_sync(2, 256);
         }
-        build_matrix<DGRAD>(cx, P, g, t0, 256);
+        if (!(P.dbg & 1)) build_matrix<DGRAD>(cx, P, g, pp.delta, pp.kb, t0, 256);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(cx.bar(B_B_FULL));
@@ -229,27 +243,26 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
   } else if (warp >= 4) {
     // ================= epilogue: thread = image row = TMEM lane =================
     const int e = warp - 4, L = e * 32 + lane;
+    const int te = tid - 128;                                     // 0..127 inside the epilogue group
     const uint32_t stg_s = cx.base + kOffStg;
     uint8_t* stg = cx.sm + kOffStg;
     float* red = reinterpret_cast<float*>(cx.sm + kOffRed);
     const uint32_t lane_off = (uint32_t)(e * 32) << 16;
-    int sc = 0;                                                   // staging slabs used so far (rotating)
     if constexpr (!DGRAD) {
-      int gc = 0;
+      // ---- forward: bf16 results through a slab of 128 rows x (128 + 16) bytes and coalesced stores ----
+      constexpr int kPitch = 144;                                 // 16-byte row stores of 8 consecutive lanes fall in 8 different bank groups
+      const bool wide = (P.P & 3) == 0;                           // planes 8-byte aligned: 4 pixels per lane, else 1
+      int gc = 0, sc = 0;
       for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
         const int c = u / P.ntile, it = u - c * P.ntile, n0 = it * 128;
-        const int cg = c / P.G, cin = (c - cg * P.G) * P.P;
-        const int n = n0 + L;
         float st_s[3] = {0.f, 0.f, 0.f}, st_q[3] = {0.f, 0.f, 0.f};
         for (int g = 0; g < 3; ++g, ++gc) {
           const int fb = gc & 1;
-          const CUtensorMap* mf = g == 0 ? &of0 : (g == 1 ? &of1 : &of2);
-          const CUtensorMap* mp = g == 0 ? &op0 : (g == 1 ? &op1 : &op2);
           mbar_wait(cx.bar(B_ACC_FULL + fb), (gc >> 1) & 1);
           tc_fence_after();
           const uint32_t ta = tmem + lane_off + fb * 256;
-          const int nchunks = nfull + ((rem8 | tail8) ? 1 : 0);
-          for (int ch = 0; ch < nchunks; ++ch) {
+          const int nchunks = (P.P + 63) >> 6;
+          for (int ch = 0; ch < nchunks; ++ch, ++sc) {
             uint32_t v[64];
             tmem_ld32(ta + 64 * ch, v); tmem_ld32(ta + 64 * ch + 32, v + 32);   // (columns beyond NPAD: never used below)
             tmem_ld_wait();
@@ -262,68 +275,48 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
             f2 s2 = 0ull, q2 = 0ull;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (2 * j < valid) {                                // (valid is even or the odd last pixel is handled below)
-                f2 a = mk2u(v[2 * j], 2 * j + 1 < valid ? v[2 * j + 1] : 0u);
+              if (2 * j < valid) {
+                const f2 a = mk2u(v[2 * j], 2 * j + 1 < valid ? v[2 * j + 1] : 0u);
                 s2 = add2(s2, a); q2 = fma2(a, a, q2);
               }
             }
             { float lo, hi; un2(s2, lo, hi); st_s[g] += lo + hi; un2(q2, lo, hi); st_q[g] += lo + hi; }
-            const bool full = ch < nfull;
-            const int bpx = full ? 64 : rem8;                     // pixels the box of this chunk stores
-            if (bpx > 0) {
-              const int slab = sc % kStgSlabs;
-              if (e == 0 && lane == 0) bulk_wait_group_read<kStgSlabs - 1>();
-              named_bar_sync(1, 128);
-              uint8_t* s0 = stg + slab * kXSlab;
-              if (full) {
+            uint8_t* s0 = stg + (sc & 1) * (128 * kPitch);
+            named_bar_sync(1, 128);                               // the copy-out of two chunks ago is complete
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  *reinterpret_cast<uint4*>(s0 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4)) =
-                      make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                 pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                 pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                 pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-              } else {                                            // unswizzled box, rows of rem8 pixels
-                const int pitch = rem8 * 2;
-#pragma unroll
-                for (int j = 0; j < 7; ++j)
-                  if (8 * j < rem8)
-                    *reinterpret_cast<uint4*>(s0 + (uint32_t)(L & 63) * pitch + (L >> 6) * (64 * pitch) + 16 * j) =
-                        make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                   pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                   pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                   pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            for (int j = 0; j < 8; ++j)
+              if (8 * j < valid)
+                *reinterpret_cast<uint4*>(s0 + (uint32_t)L * kPitch + 16 * j) =
+                    make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                               pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                               pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                               pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            named_bar_sync(1, 128);
+            __nv_bfloat16* yb = P.y[g] + ((size_t)n0 * P.C + c) * P.P + 64 * ch;    // row r: + r * C * P
+            const size_t rstride = (size_t)P.C * P.P;
+            if (P.dbg & 2) continue;
+            if (wide) {                                           // 16 lanes x 8 bytes per row, two rows per warp instruction
+              for (int i = te; i < 128 * 16; i += 128) {
+                const int r = i >> 4, q = i & 15;
+                if (4 * q < valid && n0 + r < P.N)
+                  *reinterpret_cast<uint2*>(yb + (size_t)r * rstride + 4 * q) = *reinterpret_cast<const uint2*>(s0 + r * kPitch + 8 * q);
               }
-              fence_proxy_async();
-              named_bar_sync(1, 128);
-              if (e == 0 && lane == 0) {
-                const uint32_t src = stg_s + slab * kXSlab;
-                if (full) {
-                  tma_store_3d(mf, src, cin + 64 * ch, cg, n0);
-                  tma_store_3d(mf, src + kBox, cin + 64 * ch, cg, n0 + 64);
-                } else {
-                  tma_store_3d(mp, src, cin + 64 * ch, cg, n0);
-                  tma_store_3d(mp, src + 64 * rem8 * 2, cin + 64 * ch, cg, n0 + 64);
-                }
-                bulk_commit_group();
+            } else {                                              // one pixel per lane, two warp instructions per row
+              for (int i = te; i < 128 * 64; i += 128) {
+                const int r = i >> 6, q = i & 63;
+                if (q < valid && n0 + r < P.N)
+                  yb[(size_t)r * rstride + q] = *reinterpret_cast<const __nv_bfloat16*>(s0 + r * kPitch + 2 * q);
               }
-              ++sc;
-            }
-            if (!full && tail8 > 0 && n < P.N) {                  // the last P % 8 pixels of the plane
-              __nv_bfloat16* yp = P.y[g] + ((size_t)n * P.C + c) * P.P + 64 * ch;
-#pragma unroll
-              for (int j = 0; j < 64; ++j)                        // (static register indices: predicated stores)
-                if (j >= rem8 && j < rem8 + tail8) yp[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
             }
           }
         }
         if (P.stats) {                                            // (sum, sum of squares) x 3 of this unit
 #pragma unroll
           for (int k2 = 0; k2 < 3; ++k2) {
-            float s = st_s[k2], q = st_q[k2];
+            float sv = st_s[k2], qv = st_q[k2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-            if (lane == 0) { red[e * 6 + 2 * k2] = s; red[e * 6 + 2 * k2 + 1] = q; }
+            for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); qv += __shfl_xor_sync(0xffffffffu, qv, o); }
+            if (lane == 0) { red[e * 6 + 2 * k2] = sv; red[e * 6 + 2 * k2 + 1] = qv; }
           }
           named_bar_sync(1, 128);
           if (e == 0 && lane < 6)
@@ -331,29 +324,27 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
           named_bar_sync(1, 128);
         }
       }
-    } else {
-      // ---- dgrad: D + addend -> dx (fp32); chunks of 32 pixels (128 bytes per row) ----
+    } else if ((P.P & 3) == 0) {
+      // ---- dgrad, 16-byte aligned fp32 rows: addend and dx through TMA boxes of 32 pixels (128 bytes per row) ----
       const int nfull32 = P.P >> 5;
-      const int rem4 = ((P.P & 31) >> 2) << 2;                    // pixels of the partial fp32 box
-      const int tail4 = P.P & 3;
-      const int nbox = nfull32 + (rem4 ? 1 : 0);                  // chunks that go through a box
-      int hl = 0;                                                 // addend boxes loaded so far (slab = hl % 3)
+      const int rem4 = P.P & 31;                                  // pixels of the partial box (a multiple of 4)
+      const int nbox = nfull32 + (rem4 ? 1 : 0);
+      int hl = 0;                                                 // boxes processed so far (slab = hl % 3)
       // prefetch cursor of the elected thread: (unit, chunk) of the next addend box to request
       int pf_u = blockIdx.x, pf_ch = 0, pf_n = 0;
       auto pf_issue = [&]() {
-        if (pf_u >= P.units || nbox == 0) return;
+        if (pf_u >= P.units) return;
         const int c = pf_u / P.ntile, n0 = (pf_u - c * P.ntile) * 128;
-        const int cgf = c / P.Gf, cinf = (c - cgf * P.Gf) * P.P;
         const int slab = pf_n % kStgSlabs;
         const uint32_t dst = stg_s + slab * kXSlab, bar = cx.bar(B_H_FULL + slab);
         if (pf_ch < nfull32) {
           mbar_expect_tx(bar, kXSlab);
-          tma_load_3d(dst, &of0, bar, cinf + 32 * pf_ch, cgf, n0);
-          tma_load_3d(dst + kBox, &of0, bar, cinf + 32 * pf_ch, cgf, n0 + 64);
+          tma_load_3d(dst, &fa_full, bar, 32 * pf_ch, c, n0);
+          tma_load_3d(dst + kBox, &fa_full, bar, 32 * pf_ch, c, n0 + 64);
         } else {
           mbar_expect_tx(bar, 128 * rem4 * 4);
-          tma_load_3d(dst, &op0, bar, cinf + 32 * pf_ch, cgf, n0);
-          tma_load_3d(dst + 64 * rem4 * 4, &op0, bar, cinf + 32 * pf_ch, cgf, n0 + 64);
+          tma_load_3d(dst, &fa_part, bar, 32 * pf_ch, c, n0);
+          tma_load_3d(dst + 64 * rem4 * 4, &fa_part, bar, 32 * pf_ch, c, n0 + 64);
         }
         ++pf_n;
         if (++pf_ch == nbox) { pf_ch = 0; pf_u += gridDim.x; }
@@ -362,13 +353,73 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
       int uit = 0;
       for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++uit) {
         const int c = u / P.ntile, n0 = (u - c * P.ntile) * 128;
-        const int cgf = c / P.Gf, cinf = (c - cgf * P.Gf) * P.P;
+        const int ab = uit & 1;
+        mbar_wait(cx.bar(B_ACC_FULL + ab), (uit >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ta = tmem + lane_off + ab * 256;
+        for (int ch = 0; ch < nbox; ++ch, ++hl) {
+          uint32_t v[32];
+          tmem_ld32(ta + 32 * ch, v);
+          tmem_ld_wait();
+          if (ch == nbox - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.bar(B_ACC_EMPTY + ab));
+          }
+          const bool full = ch < nfull32;
+          const int slab = hl % kStgSlabs;
+          mbar_wait(cx.bar(B_H_FULL + slab), (hl / kStgSlabs) & 1);
+          uint8_t* s0 = stg + slab * kXSlab;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4* p4 = reinterpret_cast<float4*>(s0 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4));
+              float4 a = *p4;
+              a.x += __uint_as_float(v[4 * j]); a.y += __uint_as_float(v[4 * j + 1]);
+              a.z += __uint_as_float(v[4 * j + 2]); a.w += __uint_as_float(v[4 * j + 3]);
+              *p4 = a;
+            }
+          } else {
+            const int pitch = rem4 * 4;
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+              if (4 * j < rem4) {
+                float4* p4 = reinterpret_cast<float4*>(s0 + (uint32_t)(L & 63) * pitch + (L >> 6) * (64 * pitch) + 16 * j);
+                float4 a = *p4;
+                a.x += __uint_as_float(v[4 * j]); a.y += __uint_as_float(v[4 * j + 1]);
+                a.z += __uint_as_float(v[4 * j + 2]); a.w += __uint_as_float(v[4 * j + 3]);
+                *p4 = a;
+              }
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (e == 0 && lane == 0) {
+            const uint32_t src = stg_s + slab * kXSlab;
+            if (full) {
+              tma_store_3d(&fd_full, src, 32 * ch, c, n0);
+              tma_store_3d(&fd_full, src + kBox, 32 * ch, c, n0 + 64);
+            } else {
+              tma_store_3d(&fd_part, src, 32 * ch, c, n0);
+              tma_store_3d(&fd_part, src + 64 * rem4 * 4, 32 * ch, c, n0 + 64);
+            }
+            bulk_commit_group();
+            bulk_wait_group_read<1>();          // the store before this one has let go of its slab: the addend two boxes ahead goes there
+            pf_issue();
+          }
+        }
+      }
+      if (e == 0 && lane == 0) bulk_wait_group_read<0>();
+    } else {
+      // ---- dgrad, unaligned fp32 rows (7 x 7): every thread adds and stores its own row ----
+      int uit = 0;
+      for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++uit) {
+        const int c = u / P.ntile, n0 = (u - c * P.ntile) * 128;
         const int n = n0 + L;
         const int ab = uit & 1;
         mbar_wait(cx.bar(B_ACC_FULL + ab), (uit >> 1) & 1);
         tc_fence_after();
         const uint32_t ta = tmem + lane_off + ab * 256;
-        const int nchunks = nbox + ((tail4 && !rem4) ? 1 : 0);
+        const int nchunks = (P.P + 31) >> 5;
         for (int ch = 0; ch < nchunks; ++ch) {
           uint32_t v[32];
           tmem_ld32(ta + 32 * ch, v);
@@ -378,60 +429,19 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) mbar_arrive(cx.bar(B_ACC_EMPTY + ab));
           }
-          const bool full = ch < nfull32;
-          const int bpx = full ? 32 : rem4;
-          if (bpx > 0) {
-            const int slab = hl % kStgSlabs;
-            mbar_wait(cx.bar(B_H_FULL + slab), (hl / kStgSlabs) & 1);
-            uint8_t* s0 = stg + slab * kXSlab;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4* p = reinterpret_cast<float4*>(s0 + (uint32_t)L * 128 + ((j ^ (L & 7)) << 4));
-                float4 a = *p;
-                a.x += __uint_as_float(v[4 * j]); a.y += __uint_as_float(v[4 * j + 1]);
-                a.z += __uint_as_float(v[4 * j + 2]); a.w += __uint_as_float(v[4 * j + 3]);
-                *p = a;
-              }
-            } else {
-              const int pitch = rem4 * 4;
-#pragma unroll
-              for (int j = 0; j < 7; ++j)
-                if (4 * j < rem4) {
-                  float4* p = reinterpret_cast<float4*>(s0 + (uint32_t)(L & 63) * pitch + (L >> 6) * (64 * pitch) + 16 * j);
-                  float4 a = *p;
-                  a.x += __uint_as_float(v[4 * j]); a.y += __uint_as_float(v[4 * j + 1]);
-                  a.z += __uint_as_float(v[4 * j + 2]); a.w += __uint_as_float(v[4 * j + 3]);
-                  *p = a;
-                }
-            }
-            fence_proxy_async();
-            named_bar_sync(1, 128);
-            if (e == 0 && lane == 0) {
-              const uint32_t src = stg_s + slab * kXSlab;
-              if (full) {
-                tma_store_3d(&of1, src, cinf + 32 * ch, cgf, n0);
-                tma_store_3d(&of1, src + kBox, cinf + 32 * ch, cgf, n0 + 64);
-              } else {
-                tma_store_3d(&op1, src, cinf + 32 * ch, cgf, n0);
-                tma_store_3d(&op1, src + 64 * rem4 * 4, cinf + 32 * ch, cgf, n0 + 64);
-              }
-              bulk_commit_group();
-              bulk_wait_group_read<1>();        // the store before this one has let go of its slab: the addend two boxes ahead goes there
-              pf_issue();
-            }
-            ++hl;
-          }
-          if (!full && tail4 > 0 && n < P.N) {                    // the last P % 4 pixels of the plane
+          const int valid = min(32, P.P - 32 * ch);
+          if (n < P.N) {
             const size_t off = ((size_t)n * P.C + c) * P.P + 32 * ch;
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = j < valid ? __ldg(P.addend + off + j) : 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j >= rem4 && j < rem4 + tail4) P.dx[off + j] = P.addend[off + j] + __uint_as_float(v[j]);
+              if (j < valid) P.dx[off + j] = a[j] + __uint_as_float(v[j]);
           }
         }
       }
     }
-    if (e == 0 && lane == 0) bulk_wait_group_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -469,9 +479,9 @@ static int make_map(CUtensorMap* m, const void* t, bool f32, int N, int C, int P
   SLAK_REQUIRE(r == CUDA_SUCCESS, SLAK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return SLAK_OK;
 }
-static int group_of(int Pp, int es, int C) {               // planes per tensor-map row: row bytes a multiple of 16
+static int group_of(int Pp, int C) {                       // planes per tensor-map row: row bytes a multiple of 16
   for (int G = 1; G <= 8; G <<= 1)
-    if ((G * Pp * es) % 16 == 0) return (C % G == 0) ? G : 0;
+    if ((G * Pp * 2) % 16 == 0) return (C % G == 0) ? G : 0;
   return 0;
 }
 static bool enabled() {
@@ -482,13 +492,15 @@ bool supported(int N, int C, int H, int W, int KL) {
   const int Pp = H * W;
   if (!enabled() || N < 1 || H < 1 || W < 1 || H > 16 || W > 16 || Pp > 208 || Pp < 8) return false;
   if (!(KL & 1) || KL < 5 || KL > 99) return false;
-  return group_of(Pp, 2, C) != 0 && group_of(Pp, 4, C) != 0;
+  return group_of(Pp, C) != 0;
 }
 static void fill(Params* P, int N, int C, int H, int W, int KL) {
   P->N = N; P->C = C; P->H = H; P->W = W; P->KL = KL; P->P = H * W;
-  P->G = group_of(P->P, 2, C); P->Gf = group_of(P->P, 4, C);
+  P->G = group_of(P->P, C); P->Gf = 1;
   P->NK = (P->P + 15) / 16; P->KB = (P->P + 63) / 64; P->NPAD = P->NK * 16;
   P->ntile = (N + 127) / 128; P->units = C * P->ntile;
+  const char* d = getenv("SLAK_DENSE_DBG");
+  P->dbg = d ? atoi(d) : 0;
 }
 int stats_slots(int N) { return (N + 127) / 128; }
 
@@ -500,22 +512,17 @@ int fwd(const void* x, const float* w1, const float* w2, const float* w3, void* 
   P.w[0] = w1; P.w[1] = w2; P.w[2] = w3;
   P.y[0] = (__nv_bfloat16*)y1; P.y[1] = (__nv_bfloat16*)y2; P.y[2] = (__nv_bfloat16*)y3;
   P.stats = stats;
-  const int rem8 = ((P.P & 63) >> 3) << 3;
-  CUtensorMap in, of[3], op[3];
-  memset(&in, 0, sizeof(in)); memset(of, 0, sizeof(of)); memset(op, 0, sizeof(op));
+  SLAK_REQUIRE(((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(y2) | reinterpret_cast<uintptr_t>(y3)) & 15) == 0,
+               SLAK_ERR_BAD_ARG, "outputs must be 16-byte aligned");
+  CUtensorMap in;
+  memset(&in, 0, sizeof(in));
   int rc = make_map(&in, x, false, N, C, P.P, P.G, 64, true);
   if (rc) return rc;
-  void* ys[3] = {y1, y2, y3};
-  for (int b = 0; b < 3; ++b) {
-    SLAK_REQUIRE((reinterpret_cast<uintptr_t>(ys[b]) & 15) == 0, SLAK_ERR_BAD_ARG, "outputs must be 16-byte aligned");
-    if ((rc = make_map(&of[b], ys[b], false, N, C, P.P, P.G, 64, true))) return rc;
-    if ((rc = make_map(&op[b], ys[b], false, N, C, P.P, P.G, rem8 ? rem8 : 8, false))) return rc;
-  }
   int grid = sm_count();
   if (grid > P.units) grid = P.units;
   auto kern = dense_kernel<false>;
   SLAK_SET_MAX_SMEM(kern, kSmem);
-  kern<<<grid, kThreads, kSmem, st>>>(in, in, in, of[0], of[1], of[2], op[0], op[1], op[2], P);
+  kern<<<grid, kThreads, kSmem, st>>>(in, in, in, in, in, in, in, P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
@@ -529,25 +536,28 @@ int dgrad(const void* dy1, const void* dy2, const void* dy3, const float* w1, co
   fill(&P, N, C, H, W, KL);
   P.w[0] = w1; P.w[1] = w2; P.w[2] = w3;
   P.addend = addend; P.dx = dx;
-  const int rem4 = ((P.P & 31) >> 2) << 2;
-  CUtensorMap in[3], of[2], op[2];
-  memset(in, 0, sizeof(in)); memset(of, 0, sizeof(of)); memset(op, 0, sizeof(op));
+  CUtensorMap in[3], fa[2], fd[2];
+  memset(in, 0, sizeof(in)); memset(fa, 0, sizeof(fa)); memset(fd, 0, sizeof(fd));
   const void* dys[3] = {dy1, dy2, dy3};
   int rc;
   for (int b = 0; b < 3; ++b) {
     SLAK_REQUIRE((reinterpret_cast<uintptr_t>(dys[b]) & 15) == 0, SLAK_ERR_BAD_ARG, "inputs must be 16-byte aligned");
     if ((rc = make_map(&in[b], dys[b], false, N, C, P.P, P.G, 64, true))) return rc;
   }
-  const void* ft[2] = {addend, dx};
-  for (int k = 0; k < 2; ++k) {
-    if ((rc = make_map(&of[k], ft[k], true, N, C, P.P, P.Gf, 32, true))) return rc;
-    if ((rc = make_map(&op[k], ft[k], true, N, C, P.P, P.Gf, rem4 ? rem4 : 4, false))) return rc;
+  if ((P.P & 3) == 0) {                                       // fp32 rows of P * 4 bytes are 16-byte aligned: TMA boxes
+    const int rem4 = P.P & 31;
+    if ((rc = make_map(&fa[0], addend, true, N, C, P.P, 1, 32 < P.P ? 32 : P.P, true))) return rc;
+    if ((rc = make_map(&fd[0], dx, true, N, C, P.P, 1, 32 < P.P ? 32 : P.P, true))) return rc;
+    if ((rc = make_map(&fa[1], addend, true, N, C, P.P, 1, rem4 ? rem4 : 4, false))) return rc;
+    if ((rc = make_map(&fd[1], dx, true, N, C, P.P, 1, rem4 ? rem4 : 4, false))) return rc;
+  } else {
+    fa[0] = fa[1] = fd[0] = fd[1] = in[0];                    // unused
   }
   int grid = sm_count();
   if (grid > P.units) grid = P.units;
   auto kern = dense_kernel<true>;
   SLAK_SET_MAX_SMEM(kern, kSmem);
-  kern<<<grid, kThreads, kSmem, st>>>(in[0], in[1], in[2], of[0], of[1], of[1], op[0], op[1], op[1], P);
+  kern<<<grid, kThreads, kSmem, st>>>(in[0], in[1], in[2], fa[0], fa[1], fd[0], fd[1], P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }
