@@ -19,8 +19,9 @@
 // Results leave through a shared-memory slab and coalesced 8- or 2-byte stores (bf16), or TMA boxes where rows are
 // 16-byte aligned (the fp32 gradient of 14 x 14 planes).
 //
-// One CTA = 512 threads: w0 TMA producer + MMA issuer (one thread) | w1 TMEM allocator | w4-7 epilogue (thread = image row =
-// TMEM lane) | w8-15 matrix builders.  Work unit = (channel, tile of 128 images), round-robin over a persistent grid.
+// One CTA = 640 threads: w0 MMA issuer (one thread) | w1 TMEM allocator, then TMA producer (one thread) | w4-7 and w16-19
+// epilogue (thread = image row = TMEM lane; the forward kernel splits a tile's 32-pixel chunks between the two sets) |
+// w8-15 matrix builders.  Work unit = (channel, tile of 128 images), round-robin over a persistent grid.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string.h>
@@ -30,7 +31,7 @@ namespace slak {
 namespace tc {
 namespace dense {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;                    // 20 warps: see the role list above
 constexpr int kBox = 64 * 128;                   // one TMA box: 64 rows x 128 bytes
 constexpr int kXSlab = 2 * kBox;                 // 128 images x 64 pixels (bf16)
 constexpr int kMaxKB = 4;                        // K blocks of 64 pixels: P <= 208 (13 k16 steps)
@@ -40,10 +41,10 @@ constexpr int kOffB = kOffX + kMaxKB * kXSlab;                       // 65536
 constexpr int kOffStg = kOffB + kMaxNpad * kMaxKB * 128;             // + 106496
 constexpr int kStgSlabs = 3;                                         // staging slabs of 128 rows x 128 bytes
 constexpr int kOffTaps = kOffStg + kStgSlabs * kXSlab;               // + 49152
-constexpr int kTapBytes = (2 * 99 * 5 + 25) * 4 + 12;                // KL <= 99
-constexpr int kOffHW = kOffTaps + ((kTapBytes + 15) & ~15);          // pixel -> (h, w) bytes, 2 x 256
-constexpr int kOffRed = kOffHW + 512;                                // statistics scratch [4 warps][6]
-constexpr int kOffBar = kOffRed + 128;
+constexpr int kTapBuf = 2048;                                        // one channel's taps as bf16: (2*99*5 + 25) * 2 bytes
+constexpr int kOffHW = kOffTaps + 2 * kTapBuf;                       // pixel -> (h, w) bytes, 2 x 256
+constexpr int kOffRed = kOffHW + 512;                                // statistics scratch [8 warps][6]
+constexpr int kOffBar = kOffRed + 256;
 constexpr int kSmem = kOffBar + 256 + 1024;
 static_assert(kSmem <= 232448, "shared memory budget");
 
@@ -61,7 +62,8 @@ struct Params {
 };
 
 // barrier indices
-enum { B_X_FULL = 0, B_X_EMPTY, B_B_FULL, B_B_EMPTY, B_ACC_FULL, B_ACC_EMPTY = B_ACC_FULL + 2, B_H_FULL = B_ACC_EMPTY + 2, B_COUNT = B_H_FULL + kStgSlabs };
+// barrier indices (operand buffers: three of each when a tile is a single 64-pixel K block, else one)
+enum { B_X_FULL = 0, B_X_EMPTY = 3, B_B_FULL = 6, B_B_EMPTY = 9, B_ACC_FULL = 12, B_ACC_EMPTY = 14, B_H_FULL = 16, B_COUNT = 19 };
 
 struct Ctx {
   uint8_t* sm;
@@ -75,15 +77,15 @@ struct Ctx {
 // one item = (row n, image row r of the other side): a run of <= min(kw, W) consecutive k whose taps are consecutive too
 // (ascending for the forward matrix, descending for its transpose).  Taps sit in shared memory as bf16 already.
 template <bool DGRAD>
-__device__ __forceinline__ void build_matrix(const Ctx& cx, const Params& P, int b, int delta, int kbu, int t0, int nthr) {
-  const unsigned short* taps = reinterpret_cast<const unsigned short*>(cx.sm + kOffTaps);
+__device__ __forceinline__ void build_matrix(const Ctx& cx, const Params& P, int b, int delta, int kbu, uint8_t* Bs, int tapbuf,
+                                             int t0, int nthr) {
+  const unsigned short* taps = reinterpret_cast<const unsigned short*>(cx.sm + kOffTaps + tapbuf * kTapBuf);
   const uint8_t* hh = cx.sm + kOffHW;
   const uint8_t* ww = hh + 256;
   const int KL = P.KL, Hh = P.H, Ww = P.W;
   const unsigned short* tb = b == 0 ? taps : (b == 1 ? taps + KL * 5 : taps + 2 * KL * 5);
   const int kh = b == 0 ? KL : 5, kw = b == 1 ? KL : 5;
   const int ph = kh / 2, pw = kw / 2;
-  uint8_t* Bs = cx.sm + kOffB;
   const int slab = P.NPAD * 128;
   {
     const int nvec = kbu * P.NPAD * 8;
@@ -110,8 +112,8 @@ __device__ __forceinline__ void build_matrix(const Ctx& cx, const Params& P, int
   }
 }
 
-__device__ __forceinline__ void load_taps(const Ctx& cx, const Params& P, int c, int t0, int nthr) {
-  unsigned short* taps = reinterpret_cast<unsigned short*>(cx.sm + kOffTaps);
+__device__ __forceinline__ void load_taps(const Ctx& cx, const Params& P, int c, int tapbuf, int t0, int nthr) {
+  unsigned short* taps = reinterpret_cast<unsigned short*>(cx.sm + kOffTaps + tapbuf * kTapBuf);
   const int n1 = P.KL * 5;
   for (int i = t0; i < 2 * n1 + 25; i += nthr) {
     float v;
@@ -151,12 +153,18 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
   cx.bar0 = cx.base + kOffBar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cx.sm + kOffBar + 192);
+  // a tile of one 64-pixel K block (planes of <= 57 pixels): three A buffers and three matrix buffers, so that the loads
+  // and the builds of a unit's three branches (and of the next unit) run ahead of the MMAs; larger planes: one of each
+  const int nb = P.KB == 1 ? 3 : 1;
+  const uint32_t xbuf_bytes = (uint32_t)P.KB * kXSlab, bbuf_bytes = (uint32_t)P.NPAD * P.KB * 128;
 
   if (tid == 0) {
-    mbar_init(cx.bar(B_X_FULL), 1); mbar_init(cx.bar(B_X_EMPTY), 1);
-    mbar_init(cx.bar(B_B_FULL), 8); mbar_init(cx.bar(B_B_EMPTY), 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(cx.bar(B_ACC_FULL + a), 1); mbar_init(cx.bar(B_ACC_EMPTY + a), 4); }
-    for (int sl = 0; sl < kStgSlabs; ++sl) mbar_init(cx.bar(B_H_FULL + sl), 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(cx.bar(B_X_FULL + i), 1); mbar_init(cx.bar(B_X_EMPTY + i), 1);
+      mbar_init(cx.bar(B_B_FULL + i), 8); mbar_init(cx.bar(B_B_EMPTY + i), 1);
+      mbar_init(cx.bar(B_H_FULL + i), 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(cx.bar(B_ACC_FULL + a), 1); mbar_init(cx.bar(B_ACC_EMPTY + a), DGRAD ? 4 : 8); }
     mbar_fence_init();
     tma_prefetch_desc(&in0);
     if (DGRAD) { tma_prefetch_desc(&in1); tma_prefetch_desc(&in2); tma_prefetch_desc(&fa_full); tma_prefetch_desc(&fd_full); }
@@ -172,28 +180,38 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= TMA producer + MMA issuer (one thread) =================
+  if (warp == 1) {
+    // ================= TMA producer: A tiles in consumption order (forward: x once per unit; dgrad: dy_g per group) =================
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, P.NPAD);
-      int gc = 0, ld = 0, uit = 0;                                // groups issued, A loads issued, units done
-      for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++uit) {
+      int la = 0;
+      for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
         const int c = u / P.ntile, n0 = (u - c * P.ntile) * 128;
         const PlanePos pp = plane_pos(P, c);
+        for (int g = 0; g < (DGRAD ? 3 : 1); ++g, ++la) {
+          const int xb = la % nb;
+          mbar_wait(cx.bar(B_X_EMPTY + xb), ((la / nb) & 1) ^ 1);
+          mbar_expect_tx(cx.bar(B_X_FULL + xb), (uint32_t)pp.kb * kXSlab);
+          const CUtensorMap* m = DGRAD ? (g == 0 ? &in0 : (g == 1 ? &in1 : &in2)) : &in0;
+          const uint32_t dst = cx.base + kOffX + xb * xbuf_bytes;
+          for (int kb = 0; kb < pp.kb; ++kb) {
+            tma_load_3d(dst + kb * kXSlab, m, cx.bar(B_X_FULL + xb), pp.c0 + kb * 64, pp.cg, n0);
+            tma_load_3d(dst + kb * kXSlab + kBox, m, cx.bar(B_X_FULL + xb), pp.c0 + kb * 64, pp.cg, n0 + 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
+    // ================= MMA issuer (one thread) =================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, P.NPAD);
+      int gc = 0, la = 0, uit = 0;                                // groups issued, A tiles consumed, units done
+      for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++uit) {
+        const PlanePos pp = plane_pos(P, u / P.ntile);
         const int ab = DGRAD ? (uit & 1) : 0;
         for (int g = 0; g < 3; ++g, ++gc) {
-          if (DGRAD || g == 0) {                                   // A operand: dy_g (dgrad) / x (forward, once per unit)
-            mbar_wait(cx.bar(B_X_EMPTY), (ld & 1) ^ 1);
-            mbar_expect_tx(cx.bar(B_X_FULL), (uint32_t)pp.kb * kXSlab);
-            const CUtensorMap* m = DGRAD ? (g == 0 ? &in0 : (g == 1 ? &in1 : &in2)) : &in0;
-            for (int kb = 0; kb < pp.kb; ++kb) {
-              tma_load_3d(cx.base + kOffX + kb * kXSlab, m, cx.bar(B_X_FULL), pp.c0 + kb * 64, pp.cg, n0);
-              tma_load_3d(cx.base + kOffX + kb * kXSlab + kBox, m, cx.bar(B_X_FULL), pp.c0 + kb * 64, pp.cg, n0 + 64);
-            }
-            mbar_wait(cx.bar(B_X_FULL), ld & 1);
-            ++ld;
-          }
-          mbar_wait(cx.bar(B_B_FULL), gc & 1);
+          const int xb = la % nb, bb = gc % nb;
+          if (DGRAD || g == 0) mbar_wait(cx.bar(B_X_FULL + xb), (la / nb) & 1);
+          mbar_wait(cx.bar(B_B_FULL + bb), (gc / nb) & 1);
           uint32_t acc;
           if (DGRAD) {
             if (g == 0) mbar_wait(cx.bar(B_ACC_EMPTY + ab), ((uit >> 1) & 1) ^ 1);
@@ -204,124 +222,148 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
             acc = tmem + fb * 256;
           }
           tc_fence_after();
+          const uint32_t xa = cx.base + kOffX + xb * xbuf_bytes, ba = cx.base + kOffB + bb * bbuf_bytes;
           for (int ks = 0; ks < pp.nk; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
-            umma_bf16(acc, umma_desc_k_sw128(cx.base + kOffX + kb * kXSlab + kk * 32, 0),
-                      umma_desc_k_sw128(cx.base + kOffB + kb * (P.NPAD * 128) + kk * 32, 0), idesc, DGRAD ? ((g | ks) != 0) : (ks != 0));
+            umma_bf16(acc, umma_desc_k_sw128(xa + kb * kXSlab + kk * 32, 0), umma_desc_k_sw128(ba + kb * (P.NPAD * 128) + kk * 32, 0),
+                      idesc, DGRAD ? ((g | ks) != 0) : (ks != 0));
           }
-          umma_commit(cx.bar(B_B_EMPTY));
+          umma_commit(cx.bar(B_B_EMPTY + bb));
           if (DGRAD) {
-            umma_commit(cx.bar(B_X_EMPTY));
+            umma_commit(cx.bar(B_X_EMPTY + xb)); ++la;
             if (g == 2) umma_commit(cx.bar(B_ACC_FULL + ab));
           } else {
-            if (g == 2) umma_commit(cx.bar(B_X_EMPTY));
+            if (g == 2) { umma_commit(cx.bar(B_X_EMPTY + xb)); ++la; }
             umma_commit(cx.bar(B_ACC_FULL + (gc & 1)));
           }
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 16) {
     // ================= matrix builders (256 threads) =================
     const int t0 = tid - 256;
-    int gc = 0;
-    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
-      const int c = u / P.ntile;
-      const PlanePos pp = plane_pos(P, c);
+    int gc = 0, tb = 0;
+    if (blockIdx.x < P.units) load_taps(cx, P, blockIdx.x / P.ntile, 0, t0, 256);
+    for (int u = blockIdx.x; u < P.units; u += gridDim.x, tb ^= 1) {
+      const PlanePos pp = plane_pos(P, u / P.ntile);
       for (int g = 0; g < 3; ++g, ++gc) {
-        mbar_wait(cx.bar(B_B_EMPTY), (gc & 1) ^ 1);               // the previous matrix has been consumed
-        if (g == 0) {                                             // (its taps as well: they were only read while building)
-          named_bar_sync(2, 256);
-          load_taps(cx, P, c, t0, 256);
-          named_bar_sync(2, 256);
-        }
-        if (!(P.dbg & 1)) build_matrix<DGRAD>(cx, P, g, pp.delta, pp.kb, t0, 256);
+        const int bb = gc % nb;
+        mbar_wait(cx.bar(B_B_EMPTY + bb), ((gc / nb) & 1) ^ 1);   // the matrix that lived in this buffer has been consumed
+        if (!(P.dbg & 1)) build_matrix<DGRAD>(cx, P, g, pp.delta, pp.kb, cx.sm + kOffB + bb * bbuf_bytes, tb, t0, 256);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(cx.bar(B_B_FULL));
+        if (lane == 0) mbar_arrive(cx.bar(B_B_FULL + bb));
       }
+      // the next unit's taps into the other buffer (its readers are separated from these stores by the barrier inside
+      // build_matrix; the buffer being overwritten was last read two units ago)
+      if (u + gridDim.x < P.units) load_taps(cx, P, (u + gridDim.x) / P.ntile, tb ^ 1, t0, 256);
     }
-  } else if (warp >= 4) {
-    // ================= epilogue: thread = image row = TMEM lane =================
-    const int e = warp - 4, L = e * 32 + lane;
-    const int te = tid - 128;                                     // 0..127 inside the epilogue group
+  } else if (warp >= 4 && (warp < 8 || !DGRAD)) {
+    // ================= epilogue: thread = image row = TMEM lane; every warp stages and copies out its own 32 rows =================
+    const int eset = warp >= 16 ? 1 : 0;                          // forward: second set of epilogue warps (odd chunks)
+    const int e = (warp - 4) & 3, L = e * 32 + lane;
     const uint32_t stg_s = cx.base + kOffStg;
     uint8_t* stg = cx.sm + kOffStg;
     float* red = reinterpret_cast<float*>(cx.sm + kOffRed);
     const uint32_t lane_off = (uint32_t)(e * 32) << 16;
     if constexpr (!DGRAD) {
-      // ---- forward: bf16 results through a slab of 128 rows x (128 + 16) bytes and coalesced stores ----
-      constexpr int kPitch = 144;                                 // 16-byte row stores of 8 consecutive lanes fall in 8 different bank groups
+      // ---- forward: bf16 results through a per-warp slab of 32 rows x (64 + 16) bytes and coalesced stores; chunks of 32 pixels,
+      // even chunks to warps 4-7, odd chunks to warps 16-19 ----
+      constexpr int kPitch = 80;                                  // 16-byte row stores of 8 consecutive lanes: 8 different bank groups
       const bool wide = (P.P & 3) == 0;                           // planes 8-byte aligned: 4 pixels per lane, else 1
+      uint8_t* wslab = stg + (eset * 4 + e) * (2 * 32 * kPitch);  // two buffers per warp
       int gc = 0, sc = 0;
       for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
         const int c = u / P.ntile, it = u - c * P.ntile, n0 = it * 128;
-        float st_s[3] = {0.f, 0.f, 0.f}, st_q[3] = {0.f, 0.f, 0.f};
+        float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const size_t rstride = (size_t)P.C * P.P;
+        const int rows_ok = min(32, P.N - n0 - 32 * e);           // valid image rows of this warp
+        const int nchunks = (P.P + 31) >> 5;
+#pragma unroll
         for (int g = 0; g < 3; ++g, ++gc) {
           const int fb = gc & 1;
           mbar_wait(cx.bar(B_ACC_FULL + fb), (gc >> 1) & 1);
           tc_fence_after();
           const uint32_t ta = tmem + lane_off + fb * 256;
-          const int nchunks = (P.P + 63) >> 6;
-          for (int ch = 0; ch < nchunks; ++ch, ++sc) {
-            uint32_t v[64];
-            tmem_ld32(ta + 64 * ch, v); tmem_ld32(ta + 64 * ch + 32, v + 32);   // (columns beyond NPAD: never used below)
+          const int last = ((nchunks - 1 - eset) & ~1) + eset;    // this set's last chunk (may be < eset: none)
+          if (last < eset) {                                      // no chunk for this set: release the accumulator right away
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.bar(B_ACC_EMPTY + fb));
+          }
+          f2 s2 = 0ull, q2 = 0ull;
+          for (int ch = eset; ch < nchunks; ch += 2, ++sc) {
+            uint32_t v[32];
+            tmem_ld32(ta + 32 * ch, v);                           // (columns beyond NPAD: never used below)
             tmem_ld_wait();
-            if (ch == nchunks - 1) {                              // accumulator drained
+            if (ch == last) {                                     // this set has drained the accumulator
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(cx.bar(B_ACC_EMPTY + fb));
             }
-            const int valid = min(64, P.P - 64 * ch);             // pixels of this chunk
-            f2 s2 = 0ull, q2 = 0ull;
+            const int valid = min(32, P.P - 32 * ch);             // pixels of this chunk
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               if (2 * j < valid) {
                 const f2 a = mk2u(v[2 * j], 2 * j + 1 < valid ? v[2 * j + 1] : 0u);
                 s2 = add2(s2, a); q2 = fma2(a, a, q2);
               }
             }
-            { float lo, hi; un2(s2, lo, hi); st_s[g] += lo + hi; un2(q2, lo, hi); st_q[g] += lo + hi; }
-            uint8_t* s0 = stg + (sc & 1) * (128 * kPitch);
-            named_bar_sync(1, 128);                               // the copy-out of two chunks ago is complete
+            uint8_t* s0 = wslab + (sc & 1) * (32 * kPitch);
+            __syncwarp();                                         // this warp's copy-out of two chunks ago is complete (program order)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
               if (8 * j < valid)
-                *reinterpret_cast<uint4*>(s0 + (uint32_t)L * kPitch + 16 * j) =
+                *reinterpret_cast<uint4*>(s0 + (uint32_t)lane * kPitch + 16 * j) =
                     make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
                                pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
                                pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
                                pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-            named_bar_sync(1, 128);
-            __nv_bfloat16* yb = P.y[g] + ((size_t)n0 * P.C + c) * P.P + 64 * ch;    // row r: + r * C * P
-            const size_t rstride = (size_t)P.C * P.P;
+            __syncwarp();
             if (P.dbg & 2) continue;
-            if (wide) {                                           // 16 lanes x 8 bytes per row, two rows per warp instruction
-              for (int i = te; i < 128 * 16; i += 128) {
-                const int r = i >> 4, q = i & 15;
-                if (4 * q < valid && n0 + r < P.N)
-                  *reinterpret_cast<uint2*>(yb + (size_t)r * rstride + 4 * q) = *reinterpret_cast<const uint2*>(s0 + r * kPitch + 8 * q);
+            __nv_bfloat16* yb = P.y[g] + ((size_t)(n0 + 32 * e) * P.C + c) * P.P + 32 * ch;    // row r of this warp: + r * C * P
+            if (wide) {                                           // 8 lanes x 8 bytes per row, four rows per instruction
+              const int q = lane & 7, rh = lane >> 3;
+              uint2 t[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const uint2*>(s0 + (4 * i + rh) * kPitch + 8 * q);
+              if (4 * q < valid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (4 * i + rh < rows_ok) *reinterpret_cast<uint2*>(yb + (size_t)(4 * i + rh) * rstride + 4 * q) = t[i];
               }
-            } else {                                              // one pixel per lane, two warp instructions per row
-              for (int i = te; i < 128 * 64; i += 128) {
-                const int r = i >> 6, q = i & 63;
-                if (q < valid && n0 + r < P.N)
-                  yb[(size_t)r * rstride + q] = *reinterpret_cast<const __nv_bfloat16*>(s0 + r * kPitch + 2 * q);
+            } else {                                              // one pixel per lane, one instruction per row
+#pragma unroll 1
+              for (int r0 = 0; r0 < 32; r0 += 16) {
+                unsigned short t[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = *reinterpret_cast<const unsigned short*>(s0 + (r0 + i) * kPitch + 2 * lane);
+                if (lane < valid) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (r0 + i < rows_ok) reinterpret_cast<unsigned short*>(yb + (size_t)(r0 + i) * rstride)[lane] = t[i];
+                }
               }
             }
           }
+          { float lo, hi; un2(s2, lo, hi); st[2 * g] = lo + hi; un2(q2, lo, hi); st[2 * g + 1] = lo + hi; }
         }
         if (P.stats) {                                            // (sum, sum of squares) x 3 of this unit
 #pragma unroll
-          for (int k2 = 0; k2 < 3; ++k2) {
-            float sv = st_s[k2], qv = st_q[k2];
+          for (int k2 = 0; k2 < 6; ++k2) {
+            float sv = st[k2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); qv += __shfl_xor_sync(0xffffffffu, qv, o); }
-            if (lane == 0) { red[e * 6 + 2 * k2] = sv; red[e * 6 + 2 * k2 + 1] = qv; }
+            for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            if (lane == 0) red[(eset * 4 + e) * 6 + k2] = sv;
           }
-          named_bar_sync(1, 128);
-          if (e == 0 && lane < 6)
-            P.stats[((size_t)c * P.ntile + it) * 6 + lane] = red[lane] + red[6 + lane] + red[12 + lane] + red[18 + lane];
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
+          if (eset == 0 && e == 0 && lane < 6) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += red[w8 * 6 + lane];
+            P.stats[((size_t)c * P.ntile + it) * 6 + lane] = t;
+          }
+          named_bar_sync(1, 256);
         }
       }
     } else if ((P.P & 3) == 0) {
@@ -410,12 +452,15 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
       }
       if (e == 0 && lane == 0) bulk_wait_group_read<0>();
     } else {
-      // ---- dgrad, unaligned fp32 rows (7 x 7): every thread adds and stores its own row ----
+      // ---- dgrad, unaligned fp32 rows (7 x 7): per-warp slab of 32 rows x 32 pixels (fp32), lanes along the pixels ----
+      constexpr int kPitchF = 144;                                // 36 floats
+      uint8_t* wslab = stg + e * (32 * kPitchF);
       int uit = 0;
       for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++uit) {
         const int c = u / P.ntile, n0 = (u - c * P.ntile) * 128;
-        const int n = n0 + L;
         const int ab = uit & 1;
+        const size_t rstride = (size_t)P.C * P.P;
+        const int rows_ok = min(32, P.N - n0 - 32 * e);
         mbar_wait(cx.bar(B_ACC_FULL + ab), (uit >> 1) & 1);
         tc_fence_after();
         const uint32_t ta = tmem + lane_off + ab * 256;
@@ -430,15 +475,20 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
             if (lane == 0) mbar_arrive(cx.bar(B_ACC_EMPTY + ab));
           }
           const int valid = min(32, P.P - 32 * ch);
-          if (n < P.N) {
-            const size_t off = ((size_t)n * P.C + c) * P.P + 32 * ch;
-            float a[32];
+          const size_t off0 = ((size_t)(n0 + 32 * e) * P.C + c) * P.P + 32 * ch;
+          // addend rows of this warp, coalesced (lanes along the pixels), in flight while the slab is written
+          float a[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = j < valid ? __ldg(P.addend + off + j) : 0.f;
+          for (int r = 0; r < 32; ++r) a[r] = (lane < valid && r < rows_ok) ? __ldg(P.addend + off0 + (size_t)r * rstride + lane) : 0.f;
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < valid) P.dx[off + j] = a[j] + __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(wslab + (uint32_t)lane * kPitchF + 16 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (lane < valid && r < rows_ok)
+              P.dx[off0 + (size_t)r * rstride + lane] = a[r] + *reinterpret_cast<const float*>(wslab + r * kPitchF + 4 * lane);
         }
       }
     }
@@ -497,7 +547,9 @@ bool supported(int N, int C, int H, int W, int KL) {
 static void fill(Params* P, int N, int C, int H, int W, int KL) {
   P->N = N; P->C = C; P->H = H; P->W = W; P->KL = KL; P->P = H * W;
   P->G = group_of(P->P, C); P->Gf = 1;
-  P->NK = (P->P + 15) / 16; P->KB = (P->P + 63) / 64; P->NPAD = P->NK * 16;
+  int dmax = 0;                                               // largest element offset of a plane from the 16-byte boundary below it
+  for (int j = 0; j < P->G; ++j) dmax = ((j * P->P) & 7) > dmax ? ((j * P->P) & 7) : dmax;
+  P->NK = (P->P + 15) / 16; P->KB = (dmax + P->P + 63) / 64; P->NPAD = P->NK * 16;
   P->ntile = (N + 127) / 128; P->units = C * P->ntile;
   const char* d = getenv("SLAK_DENSE_DBG");
   P->dbg = d ? atoi(d) : 0;
