@@ -498,6 +498,224 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
   if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem); }
 }
 
+// MN-major SWIZZLE_128B operand descriptor and instruction descriptor (both operands MN-major), as in mlp_tc.cu
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t mlp_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ====================================================================================================================
+// Weight gradient of the three branches for planes of <= 200 pixels and batches of <= 128 images per GPU:
+//   G_b[i, o] = sum_n X[n, i] dY_b[n, o]      (one GEMM per branch and 128-row tile of i, contraction over the images)
+//   dW_b[dh + ph, dw + pw] = sum over (i, o) with i - o = (dh, dw) of G_b[i, o]
+// Both operands are MN-major exactly as TMA delivers them (rows = images, 64 pixels = 128 bytes per box row).  The
+// diagonal sums are taken by the epilogue straight from TMEM: thread = row i, every column o adds into the tap (i - o) of a
+// per-warp private array in shared memory (no two lanes of a warp share a tap for the same column); sixteen epilogue warps
+// split the columns four ways; the warps' arrays are folded in a fixed order at the end of the channel: deterministic.
+// Roles (640 threads): w0 MMA issuer | w1 TMEM allocator, then TMA producer | w4-19 epilogue.
+// ====================================================================================================================
+namespace wg {
+constexpr int kOffXw = 0;                              // x: [2 image blocks][4 pixel blocks] boxes of 64 x 128 B
+constexpr int kOffDy = 8 * kBox;                       // dy_b: the same, two buffers
+constexpr int kOffAcc = kOffDy + 2 * 8 * kBox;         // 16 warps x taps within reach of a plane: (2H-1) 5 + 5 (2W-1) + 25 <= 335 fp32
+constexpr int kAccStride = 336;
+constexpr int kOffHWw = kOffAcc + 16 * kAccStride * 4;
+constexpr int kOffBarW = kOffHWw + 512;
+constexpr int kSmemW = kOffBarW + 256 + 1024;
+enum { W_X_FULL = 0, W_X_EMPTY, W_DY_FULL, W_DY_EMPTY = W_DY_FULL + 2, W_ACC_FULL = W_DY_EMPTY + 2, W_ACC_EMPTY = W_ACC_FULL + 2 };
+}  // namespace wg
+
+struct WgradParams {
+  float* dw[3];                   // [C][KL][5], [C][5][KL], [C][5][5]
+  int N, C, H, W, KL, P, G;
+  int mtiles, pxblocks, npadw;    // 128-row tiles of i, 64-pixel blocks, MMA N
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+dense_wgrad_kernel(const __grid_constant__ CUtensorMap xm, const __grid_constant__ CUtensorMap d0, const __grid_constant__ CUtensorMap d1,
+                   const __grid_constant__ CUtensorMap d2, WgradParams P) {
+  using namespace wg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kOffBarW;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBarW + 192);
+  if (tid == 0) {
+    mbar_init(BAR(W_X_FULL), 1); mbar_init(BAR(W_X_EMPTY), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(BAR(W_DY_FULL + a), 1); mbar_init(BAR(W_DY_EMPTY + a), 1);
+      mbar_init(BAR(W_ACC_FULL + a), 1); mbar_init(BAR(W_ACC_EMPTY + a), 16);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&xm); tma_prefetch_desc(&d0); tma_prefetch_desc(&d1); tma_prefetch_desc(&d2);
+  }
+  for (int i = tid; i < 256; i += kThreads) {
+    const int h = i / P.W;
+    sm[kOffHWw + i] = (uint8_t)h;
+    sm[kOffHWw + 256 + i] = (uint8_t)(i - h * P.W);
+  }
+  for (int i = tid; i < 16 * kAccStride; i += kThreads) reinterpret_cast<float*>(sm + kOffAcc)[i] = 0.f;
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int npb = P.pxblocks;
+
+  auto pos = [&](int c, int& cg, int& c0, int& delta) {
+    cg = c / P.G;
+    const int start = (c - cg * P.G) * P.P;
+    delta = start & 7;
+    c0 = start - delta;
+  };
+
+  if (warp == 1) {
+    if (elect_one()) {                                    // ---- TMA producer ----
+      int ld = 0, uit = 0;
+      for (int c = blockIdx.x; c < P.C; c += gridDim.x, ++uit) {
+        int cg, c0, delta;
+        pos(c, cg, c0, delta);
+        mbar_wait(BAR(W_X_EMPTY), (uit & 1) ^ 1);
+        mbar_expect_tx(BAR(W_X_FULL), (uint32_t)(2 * npb) * kBox);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int pb = 0; pb < npb; ++pb)
+            tma_load_3d(base + kOffXw + (kb * 4 + pb) * kBox, &xm, BAR(W_X_FULL), c0 + 64 * pb, cg, 64 * kb);
+        for (int b = 0; b < 3; ++b, ++ld) {
+          const int buf = ld & 1;
+          mbar_wait(BAR(W_DY_EMPTY + buf), ((ld >> 1) & 1) ^ 1);
+          mbar_expect_tx(BAR(W_DY_FULL + buf), (uint32_t)(2 * npb) * kBox);
+          const CUtensorMap* m = b == 0 ? &d0 : (b == 1 ? &d1 : &d2);
+          for (int kb = 0; kb < 2; ++kb)
+            for (int pb = 0; pb < npb; ++pb)
+              tma_load_3d(base + kOffDy + (buf * 8 + kb * 4 + pb) * kBox, m, BAR(W_DY_FULL + buf), c0 + 64 * pb, cg, 64 * kb);
+        }
+      }
+    }
+  } else if (warp == 0) {
+    if (elect_one()) {                                    // ---- MMA issuer ----
+      const uint32_t idesc = mlp_idesc_mn(128, P.npadw);
+      int ld = 0, ac = 0, uit = 0;
+      for (int c = blockIdx.x; c < P.C; c += gridDim.x, ++uit) {
+        mbar_wait(BAR(W_X_FULL), uit & 1);
+        for (int b = 0; b < 3; ++b, ++ld) {
+          const int buf = ld & 1;
+          mbar_wait(BAR(W_DY_FULL + buf), (ld >> 1) & 1);
+          for (int mt = 0; mt < P.mtiles; ++mt, ++ac) {
+            const int ab = ac & 1;
+            mbar_wait(BAR(W_ACC_EMPTY + ab), ((ac >> 1) & 1) ^ 1);
+            tc_fence_after();
+            for (int ks = 0; ks < 8; ++ks) {
+              const int kb = ks >> 2, kk = ks & 3;
+              umma_bf16(tmem + ab * 256, desc_mn_sw128(base + kOffXw + (kb * 4 + 2 * mt) * kBox + kk * 2048, kBox),
+                        desc_mn_sw128(base + kOffDy + (buf * 8 + kb * 4) * kBox + kk * 2048, kBox), idesc, ks != 0);
+            }
+            umma_commit(BAR(W_ACC_FULL + ab));
+          }
+          umma_commit(BAR(W_DY_EMPTY + buf));
+        }
+        umma_commit(BAR(W_X_EMPTY));
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: 16 warps; set = (warp - 4) / 4 takes the 32-column chunks ch = set, set + 4, ... ----
+    const int w16 = warp - 4, eset = w16 >> 2, e = w16 & 3;
+    const uint32_t lane_off = (uint32_t)(e * 32) << 16;
+    float* acc = reinterpret_cast<float*>(sm + kOffAcc) + w16 * kAccStride;
+    const uint8_t* hh = sm + kOffHWw;
+    const uint8_t* ww = hh + 256;
+    const int KL = P.KL;
+    const int nchunks = (P.npadw + 31) >> 5;
+    int ac = 0;
+    for (int c = blockIdx.x; c < P.C; c += gridDim.x) {
+      int cg, c0, delta;
+      pos(c, cg, c0, delta);
+      for (int b = 0; b < 3; ++b) {
+        // taps within reach of the plane: |dh| <= rh, |dw| <= rw; private array [2 rh + 1][2 rw + 1]
+        const int rh = b == 0 ? min(KL / 2, P.H - 1) : 2, rw = b == 1 ? min(KL / 2, P.W - 1) : 2;
+        const int kh = 2 * rh + 1, kw = 2 * rw + 1, ph = rh, pw = rw;
+        const int sz0 = (2 * min(KL / 2, P.H - 1) + 1) * 5, sz1 = 5 * (2 * min(KL / 2, P.W - 1) + 1);
+        float* ab_ = acc + (b == 0 ? 0 : (b == 1 ? sz0 : sz0 + sz1));
+        for (int mt = 0; mt < P.mtiles; ++mt, ++ac) {
+          const int ab = ac & 1;
+          mbar_wait(BAR(W_ACC_FULL + ab), (ac >> 1) & 1);
+          tc_fence_after();
+          const int pi = 128 * mt + e * 32 + lane - delta;        // input pixel of this row
+          const bool rowok = (unsigned)pi < (unsigned)P.P;
+          const int hi = rowok ? hh[pi] : 0, wi = rowok ? ww[pi] : 0;
+          const uint32_t ta = tmem + lane_off + ab * 256;
+          for (int ch = eset; ch < nchunks; ch += 4) {
+            uint32_t v[32];
+            tmem_ld32(ta + 32 * ch, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int po = 32 * ch + j - delta;                 // output pixel of this column
+              if ((unsigned)po < (unsigned)P.P) {                 // (uniform across the warp)
+                const int ho = hh[po], wo = ww[po];
+                const int dh = hi - ho + ph, dw = wi - wo + pw;
+                if (rowok && (unsigned)dh < (unsigned)kh && (unsigned)dw < (unsigned)kw) {
+                  ab_[dh * kw + dw] += __uint_as_float(v[j]);
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(W_ACC_EMPTY + ab));
+        }
+      }
+      // fold the sixteen private arrays (fixed order), write the channel's gradients, clear the arrays
+      named_bar_sync(1, 512);
+      const int n1 = KL * 5, ntap = 2 * n1 + 25;
+      float* all = reinterpret_cast<float*>(sm + kOffAcc);
+      {
+        const int rh0 = min(KL / 2, P.H - 1), rw1 = min(KL / 2, P.W - 1);
+        const int sz0 = (2 * rh0 + 1) * 5, sz1 = 5 * (2 * rw1 + 1);
+        for (int t = tid - 128; t < ntap; t += 512) {
+          // tap t of dw_b -> its slot in the clipped arrays (taps out of the plane's reach have zero gradient)
+          int off = -1;
+          float* dst;
+          if (t < n1) {
+            const int i = t / 5, j = t - i * 5, r = i - KL / 2 + rh0;
+            if ((unsigned)r < (unsigned)(2 * rh0 + 1)) off = r * 5 + j;
+            dst = P.dw[0] + (size_t)c * n1 + t;
+          } else if (t < 2 * n1) {
+            const int tt = t - n1, i = tt / KL, j = tt - i * KL, q = j - KL / 2 + rw1;
+            if ((unsigned)q < (unsigned)(2 * rw1 + 1)) off = sz0 + i * (2 * rw1 + 1) + q;
+            dst = P.dw[1] + (size_t)c * n1 + tt;
+          } else {
+            off = sz0 + sz1 + (t - 2 * n1);
+            dst = P.dw[2] + (size_t)c * 25 + (t - 2 * n1);
+          }
+          float sacc = 0.f;
+          if (off >= 0) {
+#pragma unroll
+            for (int w8 = 0; w8 < 16; ++w8) sacc += all[w8 * kAccStride + off];
+          }
+          *dst = sacc;
+        }
+      }
+      named_bar_sync(1, 512);
+      for (int t = tid - 128; t < 16 * kAccStride; t += 512) all[t] = 0.f;
+      named_bar_sync(1, 512);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
 // ====================================================================================================================
 // host side
 // ====================================================================================================================
@@ -610,6 +828,39 @@ int dgrad(const void* dy1, const void* dy2, const void* dy3, const float* w1, co
   auto kern = dense_kernel<true>;
   SLAK_SET_MAX_SMEM(kern, kSmem);
   kern<<<grid, kThreads, kSmem, st>>>(in[0], in[1], in[2], fa[0], fa[1], fd[0], fd[1], P);
+  SLAK_CUDA_TRY(cudaGetLastError());
+  return SLAK_OK;
+}
+
+
+bool wgrad_supported(int N, int C, int H, int W, int KL) {
+  return supported(N, C, H, W, KL) && N <= 128 && H * W <= 200;
+}
+int wgrad(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2, float* dw3, int N, int C, int H,
+          int W, int KL, cudaStream_t st) {
+  SLAK_REQUIRE(wgrad_supported(N, C, H, W, KL), SLAK_ERR_UNSUPPORTED, "dense plane wgrad: shape not covered");
+  Params Q{};
+  fill(&Q, N, C, H, W, KL);
+  int dmax = 0;
+  for (int j = 0; j < Q.G; ++j) dmax = ((j * Q.P) & 7) > dmax ? ((j * Q.P) & 7) : dmax;
+  WgradParams P{};
+  P.dw[0] = dw1; P.dw[1] = dw2; P.dw[2] = dw3;
+  P.N = N; P.C = C; P.H = H; P.W = W; P.KL = KL; P.P = Q.P; P.G = Q.G;
+  P.npadw = (Q.P + dmax + 15) / 16 * 16;
+  P.pxblocks = (Q.P + dmax + 63) / 64;
+  P.mtiles = (Q.P + dmax + 127) / 128;
+  CUtensorMap m[4];
+  memset(m, 0, sizeof(m));
+  const void* ts[4] = {x, dy1, dy2, dy3};
+  int rc;
+  for (int k = 0; k < 4; ++k) {
+    SLAK_REQUIRE((reinterpret_cast<uintptr_t>(ts[k]) & 15) == 0, SLAK_ERR_BAD_ARG, "inputs must be 16-byte aligned");
+    if ((rc = make_map(&m[k], ts[k], false, N, C, Q.P, Q.G, 64, true))) return rc;
+  }
+  int grid = sm_count();
+  if (grid > C) grid = C;
+  SLAK_SET_MAX_SMEM(dense_wgrad_kernel, wg::kSmemW);
+  dense_wgrad_kernel<<<grid, kThreads, wg::kSmemW, st>>>(m[0], m[1], m[2], m[3], P);
   SLAK_CUDA_TRY(cudaGetLastError());
   return SLAK_OK;
 }

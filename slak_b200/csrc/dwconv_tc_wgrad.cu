@@ -424,8 +424,16 @@ static int launch_wgrad(const CUtensorMap* maps, WgradParams& P, int grid, cudaS
   return SLAK_OK;
 }
 
+// dwconv_tc_dense.cu: planes of up to 200 pixels, batches of up to 128 images: dense GEMMs + diagonal sums
+namespace dense {
+bool wgrad_supported(int N, int C, int H, int W, int KL);
+int wgrad(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2, float* dw3, int N, int C, int H,
+          int W, int KL, cudaStream_t st);
+}
+
 int lk3_wgrad_tc(const void* x, const void* dy1, const void* dy2, const void* dy3, float* dw1, float* dw2,
                  float* dw3, int N, int C, int H, int W, int KL, void* workspace, cudaStream_t st) {
+  if (dense::wgrad_supported(N, C, H, W, KL)) return dense::wgrad(x, dy1, dy2, dy3, dw1, dw2, dw3, N, C, H, W, KL, st);
   const TcShape s = tc_shape(H, W);
   SLAK_REQUIRE(s.tile != 0, SLAK_ERR_UNSUPPORTED, "shape %dx%d not covered by the tensor-core path", H, W);
   CUtensorMap maps[4];

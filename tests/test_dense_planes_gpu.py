@@ -47,8 +47,11 @@ def _run(N, C, H, W, KL, seed):
     tmp = torch.empty_like(xd)
     _lib.check(lib.slak_lk_branches_bwd_data_f32(_p(dyd[0]), _p(dyd[1]), _p(dyd[2]), _p(wd[0]), _p(wd[1]), _p(wd[2]), _p(addd), _p(dx),
                                                  _p(tmp), N, C, H, W, KL, 5, st), "slak_lk_branches_bwd_data_f32")
+    dws = ops.lk_branches_backward_filter(xd, *dyd, KL, 5)
+    dws2 = ops.lk_branches_backward_filter(xd, *dyd, KL, 5)
     torch.cuda.synchronize()
-    return x, ws, dys, add, [y.cpu() for y in ys], sums.cpu().view(C, 6), dx.cpu()
+    assert all(torch.equal(a, b) for a, b in zip(dws, dws2))          # fixed-order reduction: bitwise repeatable
+    return x, ws, dys, add, [y.cpu() for y in ys], sums.cpu().view(C, 6), dx.cpu(), [d.cpu() for d in dws]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -57,7 +60,7 @@ def test_dense_planes_vs_oracle(case):
     if not ops.lk_branches_uses_tc(torch.empty(N, C, H, W, dtype=torch.bfloat16, device=DEV), KL, 5):
         pytest.skip("shape outside the tensor-core classes")
     os.environ["SLAK_DENSE_PLANES"] = "1"
-    x, ws, dys, add, ys, sums, dx = _run(N, C, H, W, KL, 7 + N + C + KL)
+    x, ws, dys, add, ys, sums, dx, dws = _run(N, C, H, W, KL, 7 + N + C + KL)
     idx = _subset(C)
     xs = x[:, idx].double()
     dx64 = add[:, idx].double().clone()
@@ -71,14 +74,16 @@ def test_dense_planes_vs_oracle(case):
         s_ref, q_ref = ref.sum((0, 2, 3)), (ref * ref).sum((0, 2, 3))
         assert torch.allclose(sums[idx, 2 * i], s_ref, rtol=2e-4, atol=2e-3 * ref.abs().max().item() * (N * H * W) ** 0.5), ("sum", i)
         assert torch.allclose(sums[idx, 2 * i + 1], q_ref, rtol=2e-4), ("sumsq", i)
-        dxi, _ = orc.grads_torch(xs, wr, dys[i][:, idx].double())
+        dxi, dwi = orc.grads_torch(xs, wr, dys[i][:, idx].double())
         dx64 += dxi
+        e = (dws[i][idx].double() - dwi).abs().max().item() / dwi.abs().max().item()
+        assert e <= 1e-4, ("dw", i, e)                            # the reference's own wgrad tolerance (test_correctness.py:90,127)
     err = (dx[:, idx].double() - dx64).abs().max().item() / dx64.abs().max().item()
     assert err <= 2e-5, ("dx", err)                           # fp32 accumulation of bf16 products, fp32 out
     # the banded-Toeplitz kernels on the same inputs
     os.environ["SLAK_DENSE_PLANES"] = "0"
     try:
-        _, _, _, _, ys0, sums0, dx0 = _run(N, C, H, W, KL, 7 + N + C + KL)
+        _, _, _, _, ys0, sums0, dx0, dws0 = _run(N, C, H, W, KL, 7 + N + C + KL)
     finally:
         os.environ["SLAK_DENSE_PLANES"] = "1"
     for a, b in zip(ys, ys0):
@@ -86,3 +91,5 @@ def test_dense_planes_vs_oracle(case):
     assert torch.allclose(sums, sums0, rtol=1e-3, atol=1e-2 * (N * H * W) ** 0.5)
     # (the banded path hands the 5 x 5 branch's partial gradient over in bf16: 2^-9 of that part)
     assert torch.allclose(dx, dx0, rtol=4e-3, atol=4e-3 * dx0.abs().max().item())
+    for a, b in zip(dws, dws0):
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-4 * b.abs().max().item())

@@ -41,8 +41,13 @@ def run(N, C, H, W, KL, reps=10):
         _lib.check(lib.slak_lk_branches_bwd_data_f32(P(d[0]), P(d[1]), P(d[2]), P(ws[0]), P(ws[1]), P(ws[2]), P(add), P(dx), P(tmp),
                                                      N, C, H, W, KL, 5, st), "dgrad")
 
+    from slak_b200 import ops
+
+    def wgrad(i):
+        ops.lk_branches_backward_filter(xs[i % nset], *dys[i % nset], KL, 5)
+
     out = {}
-    for name, f in (("fwd", fwd), ("dgrad", dgrad)):
+    for name, f in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
         f(0); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -55,8 +60,8 @@ def run(N, C, H, W, KL, reps=10):
 
 if __name__ == "__main__":
     for shape in [(128, 384, 14, 14, 47), (128, 768, 7, 7, 13)]:
-        for dense, dbg in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3)):
+        for dense, dbg in ((0, 0), (1, 0), (1, 3)):
             os.environ["SLAK_DENSE_PLANES"] = str(dense)
             os.environ["SLAK_DENSE_DBG"] = str(dbg)
             r = run(*shape)
-            print(f"N{shape[0]} C{shape[1]} {shape[2]}x{shape[3]} K{shape[4]}  dense={dense} dbg={dbg}:  fwd {r['fwd']:7.1f} us   dgrad {r['dgrad']:7.1f} us", flush=True)
+            print(f"N{shape[0]} C{shape[1]} {shape[2]}x{shape[3]} K{shape[4]}  dense={dense} dbg={dbg}:  fwd {r['fwd']:7.1f} us   dgrad {r['dgrad']:7.1f} us   wgrad {r['wgrad']:7.1f} us", flush=True)
