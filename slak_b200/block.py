@@ -86,6 +86,9 @@ def _dist_world(group=None):
 class FusedBlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, w2, w3, bw1, bw2, bw3, bb1, bb2, bb3, lnw, lnb, W1, b1, W2, b2, gamma, dp, cfg):
+        # the second output (bf16 copy for the next Block's conv) is not differentiable: without this, autograd would
+        # materialise a zero gradient of its full size (a 77 MB fill per stage-1 Block) just to hand it to backward
+        ctx.set_materialize_grads(False)
         with torch.cuda.device(x.device):
             return FusedBlockFunction._forward(ctx, x, w1, w2, w3, bw1, bw2, bw3, bb1, bb2, bb3, lnw, lnb, W1, b1, W2, b2,
                                                gamma, dp, cfg)
@@ -147,9 +150,9 @@ class FusedBlockFunction(torch.autograd.Function):
                 _ck(lib.slak_bn3_finalize_fwd(_p(sums), count, _p(count_dev), _ptr3(bw1, bw2, bw3), _ptr3(bb1, bb2, bb3),
                                               _ptr3(*rm), _ptr3(*rv), cfg["bn_eps"], cfg["bn_momentum"], C, _p(scale),
                                               _p(shift), _p(mean), _p(istd), st), "slak_bn3_finalize_fwd")
-            for nbt in cfg["num_batches_tracked"]:
-                if nbt is not None:
-                    nbt.add_(1)
+            nbts = [nbt for nbt in cfg["num_batches_tracked"] if nbt is not None]
+            if nbts:
+                torch._foreach_add_(nbts, 1)                  # one launch for the three counters
             ops._count(3)
         elif cfg.get("merged"):
             # re-parameterised layer: one kernel, x read once and the sum written once; w3 carries the merged bias.  The
@@ -225,6 +228,8 @@ class FusedBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, *unused):
+        if dout is None:                           # (gradients are not materialised: the output did not reach the loss)
+            return (None,) * 19
         with torch.cuda.device(dout.device):
             return FusedBlockFunction._backward(ctx, dout)
 

@@ -525,8 +525,9 @@ __host__ __device__ constexpr uint32_t mlp_idesc_mn(int M, int N) {
 namespace wg {
 constexpr int kOffXw = 0;                              // x: [2 image blocks][4 pixel blocks] boxes of 64 x 128 B
 constexpr int kOffDy = 8 * kBox;                       // dy_b: the same, two buffers
-constexpr int kOffAcc = kOffDy + 2 * 8 * kBox;         // 16 warps x taps within reach of a plane: (2H-1) 5 + 5 (2W-1) + 25 <= 335 fp32
-constexpr int kAccStride = 336;
+constexpr int kOffAcc = kOffDy + 2 * 8 * kBox;         // 16 warps x 2 copies (lane parity) x one branch's taps within reach of a plane
+constexpr int kAccB = 160;                             // (2*16-1) * 5 = 155 fp32 at most
+constexpr int kAccStride = 2 * kAccB;
 constexpr int kOffHWw = kOffAcc + 16 * kAccStride * 4;
 constexpr int kOffBarW = kOffHWw + 512;
 constexpr int kSmemW = kOffBarW + 256 + 1024;
@@ -641,11 +642,12 @@ dense_wgrad_kernel(const __grid_constant__ CUtensorMap xm, const __grid_constant
       int cg, c0, delta;
       pos(c, cg, c0, delta);
       for (int b = 0; b < 3; ++b) {
-        // taps within reach of the plane: |dh| <= rh, |dw| <= rw; private array [2 rh + 1][2 rw + 1]
+        // taps within reach of the plane: |dh| <= rh, |dw| <= rw; private arrays [2 rh + 1][2 rw + 1], one per lane parity:
+        // two consecutive columns are then two independent read-modify-write chains (lanes that would meet in a tap for
+        // columns j and j + 1 are neighbours, i.e. of different parity)
         const int rh = b == 0 ? min(KL / 2, P.H - 1) : 2, rw = b == 1 ? min(KL / 2, P.W - 1) : 2;
         const int kh = 2 * rh + 1, kw = 2 * rw + 1, ph = rh, pw = rw;
-        const int sz0 = (2 * min(KL / 2, P.H - 1) + 1) * 5, sz1 = 5 * (2 * min(KL / 2, P.W - 1) + 1);
-        float* ab_ = acc + (b == 0 ? 0 : (b == 1 ? sz0 : sz0 + sz1));
+        float* ab_ = acc + (lane & 1) * kAccB;
         for (int mt = 0; mt < P.mtiles; ++mt, ++ac) {
           const int ab = ac & 1;
           mbar_wait(BAR(W_ACC_FULL + ab), (ac >> 1) & 1);
@@ -653,62 +655,66 @@ dense_wgrad_kernel(const __grid_constant__ CUtensorMap xm, const __grid_constant
           const int pi = 128 * mt + e * 32 + lane - delta;        // input pixel of this row
           const bool rowok = (unsigned)pi < (unsigned)P.P;
           const int hi = rowok ? hh[pi] : 0, wi = rowok ? ww[pi] : 0;
+          // image rows this warp's 32 pixels touch (for skipping chunks out of the band's reach: branches 5 x K, 5 x 5)
+          const int p_lo = max(0, 128 * mt + e * 32 - delta), p_hi = min(P.P - 1, 128 * mt + e * 32 + 31 - delta);
+          const int wh_lo = p_lo <= p_hi ? hh[p_lo] : 0, wh_hi = p_lo <= p_hi ? hh[p_hi] : -100;
           const uint32_t ta = tmem + lane_off + ab * 256;
           for (int ch = eset; ch < nchunks; ch += 4) {
+            const int po0 = 32 * ch - delta;                      // output pixel of the chunk's first column
+            const int c_lo = max(0, po0), c_hi = min(P.P - 1, po0 + 31);
+            if (c_lo > c_hi) continue;
+            if ((int)hh[c_hi] < wh_lo - rh || (int)hh[c_lo] > wh_hi + rh) continue;     // no (row, column) pair within reach
             uint32_t v[32];
             tmem_ld32(ta + 32 * ch, v);
             tmem_ld_wait();
+            int ho = hh[c_lo], wo = ww[c_lo];                     // walked along the columns: no table reads in the loop
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int po = 32 * ch + j - delta;                 // output pixel of this column
-              if ((unsigned)po < (unsigned)P.P) {                 // (uniform across the warp)
-                const int ho = hh[po], wo = ww[po];
-                const int dh = hi - ho + ph, dw = wi - wo + pw;
-                if (rowok && (unsigned)dh < (unsigned)kh && (unsigned)dw < (unsigned)kw) {
-                  ab_[dh * kw + dw] += __uint_as_float(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+              int idx[2];
+              bool on[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const int po = po0 + j + t;
+                on[t] = false; idx[t] = 0;
+                if (po >= c_lo && po <= c_hi) {                   // (uniform across the warp)
+                  const int dh = hi - ho + ph, dw = wi - wo + pw;
+                  on[t] = rowok && (unsigned)dh < (unsigned)kh && (unsigned)dw < (unsigned)kw;
+                  idx[t] = dh * kw + dw;
+                  if (++wo == P.W) { wo = 0; ++ho; }
                 }
               }
+              const float a0 = on[0] ? ab_[idx[0]] : 0.f, a1 = on[1] ? ab_[idx[1]] : 0.f;
+              if (on[0]) ab_[idx[0]] = a0 + __uint_as_float(v[j]);
+              if (on[1]) ab_[idx[1]] = a1 + __uint_as_float(v[j + 1]);
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(W_ACC_EMPTY + ab));
         }
-      }
-      // fold the sixteen private arrays (fixed order), write the channel's gradients, clear the arrays
-      named_bar_sync(1, 512);
-      const int n1 = KL * 5, ntap = 2 * n1 + 25;
-      float* all = reinterpret_cast<float*>(sm + kOffAcc);
-      {
-        const int rh0 = min(KL / 2, P.H - 1), rw1 = min(KL / 2, P.W - 1);
-        const int sz0 = (2 * rh0 + 1) * 5, sz1 = 5 * (2 * rw1 + 1);
-        for (int t = tid - 128; t < ntap; t += 512) {
-          // tap t of dw_b -> its slot in the clipped arrays (taps out of the plane's reach have zero gradient)
-          int off = -1;
-          float* dst;
-          if (t < n1) {
-            const int i = t / 5, j = t - i * 5, r = i - KL / 2 + rh0;
-            if ((unsigned)r < (unsigned)(2 * rh0 + 1)) off = r * 5 + j;
-            dst = P.dw[0] + (size_t)c * n1 + t;
-          } else if (t < 2 * n1) {
-            const int tt = t - n1, i = tt / KL, j = tt - i * KL, q = j - KL / 2 + rw1;
-            if ((unsigned)q < (unsigned)(2 * rw1 + 1)) off = sz0 + i * (2 * rw1 + 1) + q;
-            dst = P.dw[1] + (size_t)c * n1 + tt;
-          } else {
-            off = sz0 + sz1 + (t - 2 * n1);
-            dst = P.dw[2] + (size_t)c * 25 + (t - 2 * n1);
-          }
-          float sacc = 0.f;
-          if (off >= 0) {
+        // fold the 32 private arrays of this branch (fixed order), write the channel's gradient, clear the arrays
+        named_bar_sync(1, 512);
+        {
+          float* all = reinterpret_cast<float*>(sm + kOffAcc);
+          const int KH = b == 0 ? KL : 5, KW = b == 1 ? KL : 5;
+          float* dst = P.dw[b] + (size_t)c * KH * KW;
+          for (int t = tid - 128; t < KH * KW; t += 512) {
+            // tap t of dw_b -> its slot in the clipped array (taps out of the plane's reach have zero gradient)
+            const int i = t / KW, j = t - i * KW;
+            const int r = i - KH / 2 + rh, q = j - KW / 2 + rw;
+            float sacc = 0.f;
+            if ((unsigned)r < (unsigned)kh && (unsigned)q < (unsigned)kw) {
+              const int off = r * kw + q;
 #pragma unroll
-            for (int w8 = 0; w8 < 16; ++w8) sacc += all[w8 * kAccStride + off];
+              for (int w8 = 0; w8 < 32; ++w8) sacc += all[w8 * kAccB + off];
+            }
+            dst[t] = sacc;
           }
-          *dst = sacc;
         }
+        named_bar_sync(1, 512);
+        for (int t = tid - 128; t < 16 * kAccStride; t += 512) reinterpret_cast<float*>(sm + kOffAcc)[t] = 0.f;
+        named_bar_sync(1, 512);
       }
-      named_bar_sync(1, 512);
-      for (int t = tid - 128; t < 16 * kAccStride; t += 512) all[t] = 0.f;
-      named_bar_sync(1, 512);
     }
   }
   tc_fence_before();

@@ -39,6 +39,7 @@ def fused_downsample_supported(ln, conv, x) -> bool:
 class DownsampleFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, lnw, lnb, weight, bias, eps):
+        ctx.set_materialize_grads(False)          # no zero-filled gradient for the (non-differentiable) bf16 copy
         lib = _lib.load()
         N, C, H, W = x.shape
         Co = weight.shape[0]
@@ -72,6 +73,8 @@ class DownsampleFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _unused):
+        if dout is None:
+            return (None,) * 6
         lib = _lib.load()
         x, lnw, mean, rstd, A, Wp = ctx.saved_tensors
         N, C, H, W, Co = ctx.dims
@@ -144,6 +147,7 @@ class StemFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, lnw, lnb, eps):
+        ctx.set_materialize_grads(False)
         lib = _lib.load()
         N, Cin, H, W = x.shape
         C = weight.shape[0]
@@ -177,6 +181,8 @@ class StemFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _unused):
+        if dout is None:
+            return (None,) * 6
         lib = _lib.load()
         A, Y, lnw, mean, rstd = ctx.saved_tensors
         N, Cin, H, W, C = ctx.dims

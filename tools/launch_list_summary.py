@@ -25,7 +25,7 @@ def main():
     print(f"{sum(cnt.values())} launches, {T / 1e3:.2f} ms of kernel time (cold-cache, serialised by ncu)")
     for k, v in tot.most_common(top):
         print(f"{v / 1e3:9.3f} ms {100 * v / T:5.1f}%  x{cnt[k]:5d}  avg {v / cnt[k]:8.1f} us  {k}")
-    ours = sum(v for k, v in tot.items() if k.startswith(("void tc::", "tc::", "void blk::", "blk::", "void ln2d::", "ln2d::", "void slak", "slak", "void g2::", "g2::", "void mlp::", "mlp::")))
+    ours = sum(v for k, v in tot.items() if k.startswith(("void tc::", "tc::", "void blk::", "blk::", "void ln2d::", "ln2d::", "void slak", "slak", "void g2::", "g2::", "void mlp::", "mlp::", "void dense::", "dense::")))
     print(f"kernels of this repo: {100 * ours / T:.1f}% of the kernel time")
 
 
