@@ -107,28 +107,8 @@ __device__ __forceinline__ void build_matrix(const Ctx& cx, const Params& P, int
     const unsigned short* tp = tb + dh * kw + (DGRAD ? (wn - wlo + pw) : (wlo - wn + pw));
     uint8_t* rowp = Bs + n * 128;
     const int sw = n & 7;
-    const int len = whi - wlo + 1;                          // <= min(kw, W) <= 16
-    if (kw == 5) {
-      unsigned short t[5];
-#pragma unroll
-      for (int e = 0; e < 5; ++e) t[e] = e < len ? tp[DGRAD ? -e : e] : (unsigned short)0;
-#pragma unroll
-      for (int e = 0; e < 5; ++e)
-        if (e < len) {
-          const int kk = k + e;
-          *reinterpret_cast<unsigned short*>(rowp + (kk >> 6) * slab + ((((kk >> 3) & 7) ^ sw) << 4) + (kk & 7) * 2) = t[e];
-        }
-    } else {
-      unsigned short t[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) t[e] = e < len ? tp[DGRAD ? -e : e] : (unsigned short)0;
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (e < len) {
-          const int kk = k + e;
-          *reinterpret_cast<unsigned short*>(rowp + (kk >> 6) * slab + ((((kk >> 3) & 7) ^ sw) << 4) + (kk & 7) * 2) = t[e];
-        }
-    }
+    for (int w = wlo; w <= whi; ++w, ++k, tp += (DGRAD ? -1 : 1))
+      *reinterpret_cast<unsigned short*>(rowp + (k >> 6) * slab + ((((k >> 3) & 7) ^ sw) << 4) + (k & 7) * 2) = *tp;
   }
 }
 
@@ -313,38 +293,32 @@ dense_kernel(const __grid_constant__ CUtensorMap in0, const __grid_constant__ CU
           }
           f2 s2 = 0ull, q2 = 0ull;
           for (int ch = eset; ch < nchunks; ch += 2, ++sc) {
-            const int valid = min(32, P.P - 32 * ch);             // pixels of this chunk
-            uint8_t* s0 = wslab + (sc & 1) * (32 * kPitch);
-            uint32_t va[16], vb[16];
-            tmem_ld16(ta + 32 * ch, va);                          // (columns beyond NPAD: never used below)
-            tmem_ld_wait();
-            tmem_ld16(ta + 32 * ch + 16, vb);                     // flies while the first half is worked on
-            __syncwarp();                                         // this warp's copy-out of two chunks ago is complete (program order)
-            auto half = [&](const uint32_t (&v)[16], int c0) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (c0 + 2 * j < valid) {
-                  const f2 a = mk2u(v[2 * j], c0 + 2 * j + 1 < valid ? v[2 * j + 1] : 0u);
-                  s2 = add2(s2, a); q2 = fma2(a, a, q2);
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-                if (c0 + 8 * j < valid)
-                  *reinterpret_cast<uint4*>(s0 + (uint32_t)lane * kPitch + 2 * c0 + 16 * j) =
-                      make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                 pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                 pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                 pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-            };
-            half(va, 0);
+            uint32_t v[32];
+            tmem_ld32(ta + 32 * ch, v);                           // (columns beyond NPAD: never used below)
             tmem_ld_wait();
             if (ch == last) {                                     // this set has drained the accumulator
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(cx.bar(B_ACC_EMPTY + fb));
             }
-            half(vb, 16);
+            const int valid = min(32, P.P - 32 * ch);             // pixels of this chunk
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (2 * j < valid) {
+                const f2 a = mk2u(v[2 * j], 2 * j + 1 < valid ? v[2 * j + 1] : 0u);
+                s2 = add2(s2, a); q2 = fma2(a, a, q2);
+              }
+            }
+            uint8_t* s0 = wslab + (sc & 1) * (32 * kPitch);
+            __syncwarp();                                         // this warp's copy-out of two chunks ago is complete (program order)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (8 * j < valid)
+                *reinterpret_cast<uint4*>(s0 + (uint32_t)lane * kPitch + 16 * j) =
+                    make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                               pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                               pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                               pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
             __syncwarp();
             if (P.dbg & 2) continue;
             __nv_bfloat16* yb = P.y[g] + ((size_t)(n0 + 32 * e) * P.C + c) * P.P + 32 * ch;    // row r of this warp: + r * C * P
@@ -685,51 +659,33 @@ dense_wgrad_kernel(const __grid_constant__ CUtensorMap xm, const __grid_constant
           const int p_lo = max(0, 128 * mt + e * 32 - delta), p_hi = min(P.P - 1, 128 * mt + e * 32 + 31 - delta);
           const int wh_lo = p_lo <= p_hi ? hh[p_lo] : 0, wh_hi = p_lo <= p_hi ? hh[p_hi] : -100;
           const uint32_t ta = tmem + lane_off + ab * 256;
-          // this set's chunks ch = eset and eset + 4 (columns 128 apart: their taps cannot meet inside a warp) are walked in
-          // lockstep, 16 columns at a time: with the two lane-parity copies that makes four independent chains
-          for (int hf = 0; hf < 2; ++hf) {
-            int po0[2], c_lo[2], c_hi[2], ho[2], wo[2];
-            bool use[2];
-            uint32_t v[2][16];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int ch = eset + 4 * q;
-              po0[q] = 32 * ch + 16 * hf - delta;                 // output pixel of the first column of this half-chunk
-              c_lo[q] = max(0, po0[q]); c_hi[q] = min(P.P - 1, po0[q] + 15);
-              use[q] = ch < nchunks && c_lo[q] <= c_hi[q];
-              if (use[q] && ((int)hh[c_hi[q]] < wh_lo - rh || (int)hh[c_lo[q]] > wh_hi + rh)) use[q] = false;   // out of the band's reach
-              ho[q] = use[q] ? hh[c_lo[q]] : 0; wo[q] = use[q] ? ww[c_lo[q]] : 0;
-              if (use[q]) tmem_ld16(ta + 32 * ch + 16 * hf, v[q]);
-            }
-            if (!(use[0] || use[1])) continue;
+          for (int ch = eset; ch < nchunks; ch += 4) {
+            const int po0 = 32 * ch - delta;                      // output pixel of the chunk's first column
+            const int c_lo = max(0, po0), c_hi = min(P.P - 1, po0 + 31);
+            if (c_lo > c_hi) continue;
+            if ((int)hh[c_hi] < wh_lo - rh || (int)hh[c_lo] > wh_hi + rh) continue;     // no (row, column) pair within reach
+            uint32_t v[32];
+            tmem_ld32(ta + 32 * ch, v);
             tmem_ld_wait();
+            int ho = hh[c_lo], wo = ww[c_lo];                     // walked along the columns: no table reads in the loop
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              int idx[2][2];
-              bool on[2][2];
+            for (int j = 0; j < 32; j += 2) {
+              int idx[2];
+              bool on[2];
 #pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                  const int po = po0[q] + j + t;
-                  on[q][t] = false; idx[q][t] = 0;
-                  if (use[q] && po >= c_lo[q] && po <= c_hi[q]) {  // (uniform across the warp)
-                    const int dh = hi - ho[q] + ph, dw = wi - wo[q] + pw;
-                    on[q][t] = rowok && (unsigned)dh < (unsigned)kh && (unsigned)dw < (unsigned)kw;
-                    idx[q][t] = dh * kw + dw;
-                    if (++wo[q] == P.W) { wo[q] = 0; ++ho[q]; }
-                  }
+              for (int t = 0; t < 2; ++t) {
+                const int po = po0 + j + t;
+                on[t] = false; idx[t] = 0;
+                if (po >= c_lo && po <= c_hi) {                   // (uniform across the warp)
+                  const int dh = hi - ho + ph, dw = wi - wo + pw;
+                  on[t] = rowok && (unsigned)dh < (unsigned)kh && (unsigned)dw < (unsigned)kw;
+                  idx[t] = dh * kw + dw;
+                  if (++wo == P.W) { wo = 0; ++ho; }
                 }
-              float a[2][2];
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int t = 0; t < 2; ++t) a[q][t] = on[q][t] ? ab_[idx[q][t]] : 0.f;
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int t = 0; t < 2; ++t)
-                  if (on[q][t]) ab_[idx[q][t]] = a[q][t] + __uint_as_float(v[q][j + t]);
+              }
+              const float a0 = on[0] ? ab_[idx[0]] : 0.f, a1 = on[1] ? ab_[idx[1]] : 0.f;
+              if (on[0]) ab_[idx[0]] = a0 + __uint_as_float(v[j]);
+              if (on[1]) ab_[idx[1]] = a1 + __uint_as_float(v[j + 1]);
             }
           }
           tc_fence_before();
