@@ -210,7 +210,7 @@ SLAK_API int slak_bn3_bwd_apply(const void* du, const void* y1, const void* y2, 
                                 void* dy1, void* dy2, void* dy3, int N, int C, int HW, void* stream);
 
 /* ---------------------------------------------------------------------------
- * Downsampling layer between two stages (models/SLaK.py:283-289: LayerNorm(channels_first) -> Conv2d(k=2, s=2)) as
+ * Downsampling layer between two stages (models/SLaK.py:194-199: LayerNorm(channels_first) -> Conv2d(k=2, s=2)) as
  * LayerNorm + GEMM (csrc/block_glue2.cu): the LayerNorm writes its bf16 output as the A operand of the convolution-as-GEMM,
  * A[(n, h/2, w/2)][((h&1)*2 + (w&1))*C + c]; slak_mlp_gemm_nt / slak_mlp_gemm_tn_splitk do the convolution, its data and
  * weight gradients; the two layout kernels move between the token-major bf16 side and the fp32 NCHW residual stream.
@@ -227,7 +227,7 @@ SLAK_API int slak_nchw_to_nhwc_parts(int N, int C, int HW);
 SLAK_API int slak_nchw_to_nhwc(const float* src, void* dst_bf16, float* part, int N, int C, int HW, void* stream);
 
 /* ---------------------------------------------------------------------------
- * Stem (models/SLaK.py:277-281: Conv2d(Cin, C, k=4, s=4) -> LayerNorm(channels_first)) as patch rows + GEMM + LayerNorm over
+ * Stem (models/SLaK.py:189-193: Conv2d(Cin, C, k=4, s=4) -> LayerNorm(channels_first)) as patch rows + GEMM + LayerNorm over
  * token rows (csrc/block_glue2.cu).  slak_patchify4: A[(n,ho,wo)][ci*16 + kh*4 + kw] (bf16, K = 64, zero beyond 16*Cin) from
  * the fp32 NCHW image, Cin <= 4, H % 4 == W % 4 == 0.  slak_ln_rows_fwd: Y bf16 [N*HW][C] (GEMM output) -> LayerNorm over C
  * -> fp32 NCHW (+ bf16 copy or NULL), mean / rstd per token.  slak_ln_rows_bwd: NCHW fp32 gradient -> dY bf16 [N*HW][C];

@@ -548,6 +548,36 @@ bn3_bwd_apply_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* 
   }
 }
 
+// The same for planes whose size is not a multiple of 4 (7 x 7): the whole tensor is contiguous, so it is walked with 16-byte
+// vectors of 8 elements regardless of the plane boundaries; a vector touches at most two channels (HW >= 8).
+__global__ void __launch_bounds__(kThreads)
+bn3_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ y1,
+                          const __nv_bfloat16* __restrict__ y2, const __nv_bfloat16* __restrict__ y3,
+                          const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy1, __nv_bfloat16* __restrict__ dy2,
+                          __nv_bfloat16* __restrict__ dy3, int C, int HW, size_t total /* elements, multiple of 8 */) {
+  const size_t nvec = total / 8;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (size_t)gridDim.x * kThreads) {
+    const size_t e0 = i * 8;
+    const size_t plane = e0 / HW;
+    const int left = (int)((plane + 1) * HW - e0);            // elements of this vector inside the first plane (>= 1)
+    const int c0 = (int)(plane % C), c1 = c0 + 1 == C ? 0 : c0 + 1;
+    float d[8], a[8], b[8], e[8], o[8];
+    ld_bf16<8>(du + e0, d); ld_bf16<8>(y1 + e0, a); ld_bf16<8>(y2 + e0, b); ld_bf16<8>(y3 + e0, e);
+    float k0[9], k1[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { k0[q] = coef[q * C + c0]; k1[q] = coef[q * C + c1]; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = k < left ? fmaf(k0[0], d[k], fmaf(k0[3], a[k], k0[6])) : fmaf(k1[0], d[k], fmaf(k1[3], a[k], k1[6]));
+    st_bf16<8>(dy1 + e0, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = k < left ? fmaf(k0[1], d[k], fmaf(k0[4], b[k], k0[7])) : fmaf(k1[1], d[k], fmaf(k1[4], b[k], k1[7]));
+    st_bf16<8>(dy2 + e0, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = k < left ? fmaf(k0[2], d[k], fmaf(k0[5], e[k], k0[8])) : fmaf(k1[2], d[k], fmaf(k1[5], e[k], k1[8]));
+    st_bf16<8>(dy3 + e0, o);
+  }
+}
+
 // per-channel batch statistics from the conv kernel's per-CTA partials -> BN scale/shift (training)
 //   part: [C][splits][6] = (sum, sumsq) x 3 branches ; stats_out: [C][6] (sum, sumsq totals, for SyncBN)
 __global__ void bn3_reduce_partials_kernel(const float* __restrict__ part, int splits, int C, double* __restrict__ sums) {
@@ -1037,6 +1067,15 @@ int bn3_bwd_apply(const void* du, const void* y1, const void* y2, const void* y3
   const int vp2 = pick_vp(HW, dy1, dy2, dy3, dy1);
   if (vp2 < vp) vp = vp2;
   const size_t planes = (size_t)N * C;
+  if (vp == 1 && HW >= 8 && (planes * HW) % 8 == 0 && pick_vp(8, du, y1, y2, y3) == 8 && pick_vp(8, dy1, dy2, dy3, dy1) == 8) {
+    const size_t total = planes * HW;
+    int grid = (int)((total / 8 + kThreads - 1) / kThreads);
+    if (grid > 8 * sm_count()) grid = 8 * sm_count();
+    bn3_bwd_apply_flat_kernel<<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)du, (const __nv_bfloat16*)y1, (const __nv_bfloat16*)y2,
+        (const __nv_bfloat16*)y3, coef, (__nv_bfloat16*)dy1, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dy3, C, HW, total);
+    SLAK_CUDA_TRY(cudaGetLastError());
+    return SLAK_OK;
+  }
   const size_t total = planes * (HW / vp);
   int grid = (int)((total + kThreads - 1) / kThreads);
   if (grid > 8 * sm_count()) grid = 8 * sm_count();

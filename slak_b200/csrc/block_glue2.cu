@@ -660,7 +660,44 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16* __res
 
 
 // ====================================================================================================================
-// Downsampling layer (models/SLaK.py:283-289: channels_first LayerNorm, then Conv2d(k=2, s=2)) as LayerNorm + GEMM:
+// residual_fwd / nhwc_to_nchw for planes that are not a multiple of 4 pixels (7 x 7): a tile is CH channels x the WHOLE
+// plane, which is contiguous in NCHW -- every access of the NCHW side is a coalesced 4-byte (fp32) or 2-byte (bf16)
+// element per lane, the NHWC rows (CH channels = 128 bytes per pixel) are staged in shared memory.
+// ====================================================================================================================
+__global__ void __launch_bounds__(kThreads, 4)
+res_fwd_flat_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ h2, const float* __restrict__ gamma,
+                    const float* __restrict__ dp, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16, int N, int C, int HW,
+                    int CH) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem);          // [HW][CH + 2]
+  float* gs_ = reinterpret_cast<float*>(smem + (((size_t)HW * (CH + 2) * 2 + 15) & ~(size_t)15));   // [CH] gamma * dp
+  const int tid = threadIdx.x, pitch = CH + 2;
+  const int cchunks = C / CH, tiles = N * cchunks, tile_elems = CH * HW, vpr = CH / 8;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int n = t / cchunks, c0 = (t - n * cchunks) * CH;
+    const float dps = dp ? dp[n] : 1.f;
+    __syncthreads();
+    for (int v = tid; v < HW * vpr; v += kThreads) {
+      const int p = v / vpr, k = v - p * vpr;
+      const uint4 r = *reinterpret_cast<const uint4*>(h2 + ((size_t)n * HW + p) * C + c0 + 8 * k);
+      uint32_t* d = reinterpret_cast<uint32_t*>(hs + (size_t)p * pitch + 8 * k);
+      d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w;
+    }
+    for (int c = tid; c < CH; c += kThreads) gs_[c] = (gamma ? gamma[c0 + c] : 1.f) * dps;
+    __syncthreads();
+    const size_t base = ((size_t)n * C + c0) * HW;
+#pragma unroll 4
+    for (int e = tid; e < tile_elems; e += kThreads) {
+      const int c = e / HW, p = e - c * HW;
+      const float v = fmaf(__bfloat162float(hs[(size_t)p * pitch + c]), gs_[c], x ? x[base + e] : 0.f);
+      out[base + e] = v;
+      if (out_bf16) out_bf16[base + e] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ====================================================================================================================
+// Downsampling layer (models/SLaK.py:194-199: channels_first LayerNorm, then Conv2d(k=2, s=2)) as LayerNorm + GEMM:
 // the LayerNorm writes its output directly as the GEMM's A operand, A[token = (n, h/2, w/2)][k = ((h&1)*2 + (w&1))*C + c]
 // (bf16, one contiguous run of C channels per input pixel); the convolution is then a plain [tokens, 4C] x [4C, Cout]
 // GEMM on the tcgen05 kernels of mlp_tc.cu.  Same thread <-> data mapping as above with u = x (fp32 NCHW).
@@ -899,7 +936,7 @@ ln2d_patch_bwd_kernel(const __nv_bfloat16* __restrict__ dA, const float* __restr
 
 
 // ====================================================================================================================
-// Stem (models/SLaK.py:277-281: Conv2d(3, C, k=4, s=4) -> LayerNorm(channels_first)): patch rows of the image, the
+// Stem (models/SLaK.py:189-193: Conv2d(3, C, k=4, s=4) -> LayerNorm(channels_first)): patch rows of the image, the
 // convolution as a GEMM (mlp_tc.cu), then LayerNorm over the channels of each token row with the NCHW residual stream
 // (fp32 + bf16 copy) as output.  Backward: LayerNorm backward from the NCHW gradient to token rows (dY, bf16), the
 // weight gradient is the split-K GEMM dY^T A; the image needs no gradient.
@@ -1211,9 +1248,20 @@ int res_fwd(const float* x, const void* h2, const float* gamma, const float* dp,
   if (!make_g2(N, C, HW, &g) || (reinterpret_cast<uintptr_t>(h2) & 15) != 0) return SLAK_G2_UNSUPPORTED;
   const size_t smem = gs_bytes(g);
   const int lw = lw_of(HW, (uintptr_t)out_bf16, (uintptr_t)x | (uintptr_t)out);
-  // unaligned planes (7 x 7): 24 element-wise accesses per span, each lane in another plane -- the shared-memory-tile kernel of
-  // block_fused.cu is faster there (measured 49 vs 82 us at N128 C768); the pure transposition has no such fallback
-  if (lw == 1 && x != nullptr) return SLAK_G2_UNSUPPORTED;
+  if (lw == 1) {
+    // unaligned planes (7 x 7): element-wise accesses per span with every lane in another plane are slow; tiles of CH
+    // channels x the whole (contiguous) plane instead
+    const int CH = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8));
+    const size_t fsm = (((size_t)HW * (CH + 2) * 2 + 15) & ~(size_t)15) + (size_t)CH * sizeof(float);
+    if (fsm <= 48 * 1024) {
+      int fgrid = N * (C / CH);
+      if (fgrid > 8 * sm_count()) fgrid = 8 * sm_count();
+      res_fwd_flat_kernel<<<fgrid, kThreads, fsm, st>>>(x, (const __nv_bfloat16*)h2, gamma, dp, out, (__nv_bfloat16*)out_bf16, N, C, HW, CH);
+      SLAK_CUDA_TRY(cudaGetLastError());
+      return SLAK_OK;
+    }
+    if (x != nullptr) return SLAK_G2_UNSUPPORTED;           // (the first-generation kernel takes it; the pure transposition goes on below)
+  }
   const int grid = grid_of(g, 3);
 #define CALL(V)                                                                                                      \
   SLAK_SET_MAX_SMEM(res_fwd2_kernel<V>, smem);                                                                      \

@@ -1,4 +1,4 @@
-"""Downsampling layer between two stages (reference models/SLaK.py:283-289: LayerNorm(channels_first) followed by
+"""Downsampling layer between two stages (reference models/SLaK.py:194-199: LayerNorm(channels_first) followed by
 Conv2d(kernel_size=2, stride=2)) as ONE autograd node on this library's kernels.
 
 A 2 x 2 stride-2 convolution reads every input pixel exactly once: it is a GEMM over non-overlapping patches,
@@ -120,7 +120,7 @@ def fused_downsample(ln, conv, x):
 
 
 # ------------------------------------------------------------------------------------------------------------------------
-# Stem: Conv2d(Cin, C, kernel_size=4, stride=4) -> LayerNorm(channels_first)   (reference models/SLaK.py:277-281)
+# Stem: Conv2d(Cin, C, kernel_size=4, stride=4) -> LayerNorm(channels_first)   (reference models/SLaK.py:189-193)
 # ------------------------------------------------------------------------------------------------------------------------
 STEM_K = 64        # patch row length: 16 * Cin (<= 64) values, zero padded (one 128-byte swizzle atom of the GEMM's K loop)
 

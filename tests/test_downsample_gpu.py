@@ -1,4 +1,4 @@
-"""Downsampling layer (reference models/SLaK.py:283-289, LayerNorm(channels_first) -> Conv2d(k=2, s=2)) as one autograd node
+"""Downsampling layer (reference models/SLaK.py:194-199, LayerNorm(channels_first) -> Conv2d(k=2, s=2)) as one autograd node
 on this library's kernels (slak_b200/downsample.py) against the same two modules in fp64."""
 import pytest
 import torch
