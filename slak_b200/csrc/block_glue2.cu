@@ -86,11 +86,29 @@ __device__ __forceinline__ void ldg_span(const __nv_bfloat16* __restrict__ p, in
     if (nv > 4) b = *reinterpret_cast<const uint2*>(p + 4);
     r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
   } else {
-    const unsigned short* q = reinterpret_cast<const unsigned short*>(p);
+    // 2-byte aligned span: up to three aligned 8-byte words cover it (instead of eight 2-byte loads with every lane of the
+    // warp in another plane); only words that hold a valid element are touched, so nothing outside the tensor is read
+    // (its size in bytes is a multiple of 8: C % 8 == 0)
+    r[0] = r[1] = r[2] = r[3] = 0u;
+    if (nv > 0) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+      const int sft = (int)(a & 7);
+      const uint2* w = reinterpret_cast<const uint2*>(a - sft);
+      const int need = sft + 2 * (nv < 8 ? nv : 8);                 // bytes from the start of the first word
+      uint32_t W[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+      { const uint2 t = w[0]; W[0] = t.x; W[1] = t.y; }
+      if (need > 8) { const uint2 t = w[1]; W[2] = t.x; W[3] = t.y; }
+      if (need > 16) { const uint2 t = w[2]; W[4] = t.x; W[5] = t.y; }
+      const bool up = (sft & 4) != 0;
+      const uint32_t sh = (uint32_t)(sft & 2) * 8u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t lo = 2 * k < nv ? q[2 * k] : 0u, hi = 2 * k + 1 < nv ? q[2 * k + 1] : 0u;
-      r[k] = lo | (hi << 16);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = up ? W[k + 1] : W[k], hi = up ? W[k + 2] : W[k + 1];
+        uint32_t v = __funnelshift_r(lo, hi, sh);
+        if (2 * k >= nv) v = 0u;
+        else if (2 * k + 1 >= nv) v &= 0xffffu;
+        r[k] = v;
+      }
     }
   }
 }
@@ -1229,6 +1247,8 @@ int ln_fwd(const void* y1, const void* y2, const void* y3, const float* scale, c
            const float* lnb, float eps, void* xn, float* mu, float* rstd, int N, int C, int HW, cudaStream_t st) {
   G2 g;
   if (!make_g2(N, C, HW, &g) || (reinterpret_cast<uintptr_t>(xn) & 15) != 0) return SLAK_G2_UNSUPPORTED;
+  // (the 2-byte-aligned span loads read whole 8-byte words: the planes' tensors must start on 8 bytes)
+  if (((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(y2) | reinterpret_cast<uintptr_t>(y3)) & 7) != 0) return SLAK_G2_UNSUPPORTED;
   const size_t smem = (4096 + kThreads + 2 * (size_t)g.PIX) * sizeof(float) + (size_t)C * (sizeof(float4) + 2 * sizeof(float)) + gs_bytes(g);
   const int lw = lw_of(HW, (uintptr_t)y1 | (uintptr_t)y2 | (uintptr_t)y3, 0);
   const int grid = grid_of(g, 2);
@@ -1301,6 +1321,7 @@ int ln_bwd(const void* dxn, const void* y1, const void* y2, const void* y3, cons
            const float* lnw, const float* mu, const float* rstd, void* du, float* part, int N, int C, int HW, cudaStream_t st) {
   G2 g;
   if (!make_g2(N, C, HW, &g) || (reinterpret_cast<uintptr_t>(dxn) & 15) != 0) return SLAK_G2_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(y2) | reinterpret_cast<uintptr_t>(y3)) & 7) != 0) return SLAK_G2_UNSUPPORTED;
   const size_t smem = (size_t)3 * kItems * kThreads * sizeof(uint4) + (4096 + kThreads + 5 * (size_t)g.PIX) * sizeof(float) +
                       (size_t)C * sizeof(float4) + gs_bytes(g);
   const int lw = lw_of(HW, (uintptr_t)y1 | (uintptr_t)y2 | (uintptr_t)y3 | (uintptr_t)du, 0);
