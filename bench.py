@@ -375,7 +375,10 @@ def run_ours(args):
     UF = cfg["update_freq"]
     # data parallelism = gradient all-reduce only (main.py:374-376): flat gradient buffer, buckets all-reduced on a side
     # stream as backward produces them (slak_b200/ddp.py); identical initial weights by broadcast
-    dp = ddp.GradientAllReducer(net, bucket_mb=25.0) if world > 1 else None
+    # bucket size: measured on this step (profiles/r02_bucket_sweep.txt) -- the step is bound by the SMs and HBM, and NCCL kernels
+    # that overlap backward take both away from it: at N = 2 one 123 MB all-reduce after backward (16.37 ms) beats 25 MB
+    # buckets overlapped with it (16.64 ms); at N = 8 the two are equal (17.18 ms).  200 MB = one bucket for SLaK-T / S.
+    dp = ddp.GradientAllReducer(net, bucket_mb=float(os.environ.get("SLAK_BUCKET_MB", "200"))) if world > 1 else None
     # gradients live in one flat buffer (static addresses for the graph and for the fused optimizer's pointer tables)
     flat = dp if dp is not None else ddp.FlatGradients(net)
     if args.torch_adamw:
