@@ -1268,10 +1268,12 @@ int res_fwd(const float* x, const void* h2, const float* gamma, const float* dp,
   if (!make_g2(N, C, HW, &g) || (reinterpret_cast<uintptr_t>(h2) & 15) != 0) return SLAK_G2_UNSUPPORTED;
   const size_t smem = gs_bytes(g);
   const int lw = lw_of(HW, (uintptr_t)out_bf16, (uintptr_t)x | (uintptr_t)out);
-  if (lw == 1) {
-    // unaligned planes (7 x 7): element-wise accesses per span with every lane in another plane are slow; tiles of CH
-    // channels x the whole (contiguous) plane instead
-    const int CH = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8));
+  static const int flat_lw = [] { const char* e = getenv("SLAK_RES_FLAT_LW"); return e ? atoi(e) : 4; }();   // planes of this alignment class and below go flat (14 x 14: 34 -> 32 us, 31 -> 24 us as a pure transposition)
+  if (lw <= flat_lw) {
+    // planes that are not 16-byte aligned (7 x 7, 14 x 14): tiles of CH channels x the whole (contiguous) plane instead of
+    // spans: every NCHW access is a coalesced element per lane
+    const int CHmax = lw == 1 ? 64 : 32;
+    const int CH = (C % 64 == 0 && CHmax >= 64) ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8));
     const size_t fsm = (((size_t)HW * (CH + 2) * 2 + 15) & ~(size_t)15) + (size_t)CH * sizeof(float);
     if (fsm <= 48 * 1024) {
       int fgrid = N * (C / CH);
